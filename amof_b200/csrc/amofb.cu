@@ -1,0 +1,603 @@
+// amofb.cu -- the C ABI of libamofb.so (include/amofb.h): context, memory helpers and the three analyses.
+// Build: see amof_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off).
+#include "common.cuh"
+#include "prep.cuh"
+#include "pair.cuh"
+#include "bad.cuh"
+#include "msd.cuh"
+
+#include <algorithm>
+#include <new>
+
+// ================================================================================================
+// lifetime and helpers
+// ================================================================================================
+
+static const char *k_no_ctx = "null context";
+
+extern "C" const char *amofb_version(void) { return AMOFB_VERSION_STRING; }
+
+extern "C" const char *amofb_last_error(const amofb_ctx *ctx) { return ctx ? ctx->err.c_str() : k_no_ctx; }
+
+extern "C" int amofb_create(int device, amofb_ctx **out) {
+    if (!out) return AMOFB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return AMOFB_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= count) return AMOFB_ERR_ARG;
+    amofb_ctx *ctx = new (std::nothrow) amofb_ctx();
+    if (!ctx) return AMOFB_ERR_MEMORY;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AMOFB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return AMOFB_ERR_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return AMOFB_ERR_CUDA;
+    }
+    *out = ctx;
+    return AMOFB_OK;
+}
+
+static void pair_release(amofb_ctx *ctx);
+static void bad_release(amofb_ctx *ctx);
+static void msd_release(amofb_ctx *ctx);
+
+extern "C" int amofb_destroy(amofb_ctx *ctx) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    pair_release(ctx);
+    bad_release(ctx);
+    msd_release(ctx);
+    for (auto &p : ctx->pending_pair_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+    return AMOFB_OK;
+}
+
+static int drain_pair_events(amofb_ctx *ctx) {
+    for (auto &p : ctx->pending_pair_events) {
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventSynchronize(p.second));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, p.first, p.second));
+        ctx->pair_ms += ms;
+        ctx->pair_launches += 1;
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    ctx->pending_pair_events.clear();
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_sync(amofb_ctx *ctx) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_copy));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_sync_copies(amofb_ctx *ctx) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_copy));
+    return AMOFB_OK;
+}
+
+extern "C" int64_t amofb_launch_count(const amofb_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int amofb_set_profiling(amofb_ctx *ctx, int enabled) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    ctx->profiling = enabled != 0;
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_pair_kernel_time(amofb_ctx *ctx, double *total_ms, int64_t *launches, int reset) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    AMOFB_TRY(drain_pair_events(ctx));
+    if (total_ms) *total_ms = ctx->pair_ms;
+    if (launches) *launches = ctx->pair_launches;
+    if (reset) { ctx->pair_ms = 0.0; ctx->pair_launches = 0; }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_host_alloc(amofb_ctx *ctx, uint64_t bytes, void **out) {
+    if (!ctx || !out) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return AMOFB_OK;
+}
+extern "C" int amofb_host_free(amofb_ctx *ctx, void *ptr) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaFreeHost(ptr));
+    return AMOFB_OK;
+}
+extern "C" int amofb_device_alloc(amofb_ctx *ctx, uint64_t bytes, void **out) {
+    if (!ctx || !out) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return amofb_fail(ctx, AMOFB_ERR_MEMORY, "cudaMalloc of %llu bytes failed", (unsigned long long)bytes); }
+    CUDA_TRY(ctx, e);
+    return AMOFB_OK;
+}
+extern "C" int amofb_device_free(amofb_ctx *ctx, void *ptr) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaFree(ptr));
+    return AMOFB_OK;
+}
+extern "C" int amofb_memcpy_h2d(amofb_ctx *ctx, void *dst_device, const void *src_host, uint64_t bytes) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_copy));
+    return AMOFB_OK;
+}
+extern "C" int amofb_memcpy_d2h(amofb_ctx *ctx, void *dst_host, const void *src_device, uint64_t bytes) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->s_copy));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_copy));
+    return AMOFB_OK;
+}
+
+template <typename T>
+static int dev_alloc(amofb_ctx *ctx, T **p, size_t count) {
+    *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return amofb_fail(ctx, AMOFB_ERR_MEMORY, "device allocation of %zu bytes failed", count * sizeof(T));
+    }
+    CUDA_TRY(ctx, e);
+    return AMOFB_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+
+// ================================================================================================
+// frame batches: the streaming unit shared by the pair and bond-angle analyses
+//   raw positions (H2D on s_copy) -> cell list (3 kernels on s_compute) -> analysis kernel
+// two slots alternate so the copy of batch k+1 overlaps the kernels of batch k
+// ================================================================================================
+
+struct BatchSlot {
+    double *d_raw = nullptr;
+    FrameGeom *d_geom = nullptr, *h_geom = nullptr;
+    uint32_t *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cid = nullptr, *d_rank = nullptr;
+    SAtom *d_sorted = nullptr;
+    unsigned long long *d_out = nullptr, *h_out = nullptr;   // per-frame outputs of the batch
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+    int frames = 0;        // frames of the batch in flight (0 = idle)
+    int64_t first = 0;     // global index of its first frame
+};
+
+struct Batcher {
+    int n_atoms = 0, cap_frames = 0, per_frame_out = 0;
+    size_t cells_per_frame = 0;
+    double rcut = 0.0;
+    int cell_div = 1;
+    uint8_t *d_species = nullptr;
+    BatchSlot slot[2];
+    int next = 0;
+    int64_t frames_seen = 0;
+    double volume_sum = 0.0;
+    std::vector<unsigned long long> out_all;   // harvested per-frame outputs, frame-major
+};
+
+static void batcher_release(Batcher &b) {
+    for (auto &s : b.slot) {
+        cudaFree(s.d_raw); cudaFree(s.d_geom); cudaFreeHost(s.h_geom);
+        cudaFree(s.d_cell_count); cudaFree(s.d_cell_start); cudaFree(s.d_cid); cudaFree(s.d_rank);
+        cudaFree(s.d_sorted); cudaFree(s.d_out); cudaFreeHost(s.h_out);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        s = BatchSlot();
+    }
+    cudaFree(b.d_species);
+    b.d_species = nullptr;
+}
+
+static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *species, double rcut, int cell_div,
+                        int per_frame_out) {
+    b.n_atoms = n_atoms;
+    b.rcut = rcut;
+    b.cell_div = cell_div;
+    b.per_frame_out = per_frame_out;
+    long long target = env_int("AMOFB_BATCH_ATOMS", 1 << 20);
+    long long cap = target / std::max(n_atoms, 1);
+    b.cap_frames = (int)std::min<long long>(std::max<long long>(cap, 1), 8192);
+    b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0) + 1;
+    AMOFB_TRY(dev_alloc(ctx, &b.d_species, (size_t)n_atoms));
+    CUDA_TRY(ctx, cudaMemcpy(b.d_species, species, (size_t)n_atoms, cudaMemcpyHostToDevice));
+    size_t na = (size_t)b.cap_frames * n_atoms;
+    for (auto &s : b.slot) {
+        AMOFB_TRY(dev_alloc(ctx, &s.d_raw, na * 3));
+        AMOFB_TRY(dev_alloc(ctx, &s.d_geom, (size_t)b.cap_frames));
+        CUDA_TRY(ctx, cudaHostAlloc((void **)&s.h_geom, sizeof(FrameGeom) * b.cap_frames, cudaHostAllocDefault));
+        AMOFB_TRY(dev_alloc(ctx, &s.d_cell_count, b.cells_per_frame * b.cap_frames));
+        AMOFB_TRY(dev_alloc(ctx, &s.d_cell_start, b.cells_per_frame * b.cap_frames));
+        AMOFB_TRY(dev_alloc(ctx, &s.d_cid, na));
+        AMOFB_TRY(dev_alloc(ctx, &s.d_rank, na));
+        AMOFB_TRY(dev_alloc(ctx, &s.d_sorted, na));
+        if (per_frame_out > 0) {
+            AMOFB_TRY(dev_alloc(ctx, &s.d_out, (size_t)b.cap_frames * per_frame_out));
+            CUDA_TRY(ctx, cudaHostAlloc((void **)&s.h_out, sizeof(unsigned long long) * b.cap_frames * per_frame_out,
+                                        cudaHostAllocDefault));
+        }
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    return AMOFB_OK;
+}
+
+// wait for the slot's batch and move its per-frame outputs to out_all
+static int batcher_harvest(amofb_ctx *ctx, Batcher &b, BatchSlot &s) {
+    if (s.frames == 0) return AMOFB_OK;
+    CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
+    if (b.per_frame_out > 0) {
+        size_t need = (size_t)(s.first + s.frames) * b.per_frame_out;
+        if (b.out_all.size() < need) b.out_all.resize(need, 0ull);
+        memcpy(b.out_all.data() + (size_t)s.first * b.per_frame_out, s.h_out,
+               sizeof(unsigned long long) * (size_t)s.frames * b.per_frame_out);
+    }
+    s.frames = 0;
+    return AMOFB_OK;
+}
+
+// Stage one batch (<= cap_frames frames): geometry, H2D (or adopt a device pointer) and the cell list.
+// On return the slot's sorted atoms / cell_start are valid on s_compute; the caller enqueues its analysis kernel
+// and then calls batcher_commit.
+static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, bool pos_on_device, const double *cell,
+                         BatchSlot **out_slot, const double **out_raw) {
+    BatchSlot &s = b.slot[b.next];
+    AMOFB_TRY(batcher_harvest(ctx, b, s));
+    int cs_off = 0;
+    for (int f = 0; f < nf; ++f) {
+        FrameGeom &g = s.h_geom[f];
+        if (!host_fill_geom(g, cell + 9 * (size_t)f, b.rcut, b.cell_div, b.n_atoms))
+            return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %lld: singular cell or cell far smaller than the cutoff %g",
+                              (long long)(b.frames_seen + f), b.rcut);
+        g.cs_off = cs_off;
+        g.frame_id = (int)(b.frames_seen + f);
+        cs_off += g.ncell + 1;
+        b.volume_sum += host_cell_volume(cell + 9 * (size_t)f);
+    }
+    const double *raw = pos;
+    size_t bytes = sizeof(double) * 3 * (size_t)nf * b.n_atoms;
+    if (!pos_on_device) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_raw, pos, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+        CUDA_TRY(ctx, cudaEventRecord(s.ev_h2d, ctx->s_copy));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
+        raw = s.d_raw;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_geom, s.h_geom, sizeof(FrameGeom) * nf, cudaMemcpyHostToDevice, ctx->s_compute));
+    CUDA_TRY(ctx, cudaMemsetAsync(s.d_cell_count, 0, sizeof(uint32_t) * (size_t)cs_off, ctx->s_compute));
+    if (b.per_frame_out > 0)
+        CUDA_TRY(ctx, cudaMemsetAsync(s.d_out, 0, sizeof(unsigned long long) * (size_t)nf * b.per_frame_out, ctx->s_compute));
+    PrepArgs pa;
+    pa.raw = raw; pa.geom = s.d_geom; pa.species = b.d_species;
+    pa.cell_count = s.d_cell_count; pa.cell_start = s.d_cell_start; pa.cid = s.d_cid; pa.rank = s.d_rank;
+    pa.sorted = s.d_sorted; pa.n_atoms = b.n_atoms; pa.n_frames = nf;
+    long long total = (long long)nf * b.n_atoms;
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
+    if (blocks < 1) blocks = 1;
+    if (total > 0) {
+        k_cell_assign<<<blocks, 256, 0, ctx->s_compute>>>(pa);
+        k_cell_scan<<<nf, 1024, 0, ctx->s_compute>>>(pa);
+        k_cell_scatter<<<blocks, 256, 0, ctx->s_compute>>>(pa);
+        ctx->launches += 3;
+        CUDA_TRY(ctx, cudaGetLastError());
+    } else {
+        k_cell_scan<<<nf, 1024, 0, ctx->s_compute>>>(pa);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    *out_slot = &s;
+    *out_raw = raw;
+    return AMOFB_OK;
+}
+
+static int batcher_commit(amofb_ctx *ctx, Batcher &b, BatchSlot &s, int nf) {
+    if (b.per_frame_out > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, sizeof(unsigned long long) * (size_t)nf * b.per_frame_out,
+                                      cudaMemcpyDeviceToHost, ctx->s_compute));
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_done, ctx->s_compute));
+    s.frames = nf;
+    s.first = b.frames_seen;
+    b.frames_seen += nf;
+    b.next ^= 1;
+    return AMOFB_OK;
+}
+
+static int batcher_drain(amofb_ctx *ctx, Batcher &b) {
+    // harvest in submission order
+    BatchSlot *a = &b.slot[b.next], *c = &b.slot[b.next ^ 1];
+    AMOFB_TRY(batcher_harvest(ctx, b, *a));
+    AMOFB_TRY(batcher_harvest(ctx, b, *c));
+    return AMOFB_OK;
+}
+
+static inline int fold_key(int a, int b, int S) {
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    return lo * S - lo * (lo - 1) / 2 + (hi - lo);
+}
+
+// ================================================================================================
+// pair analysis
+// ================================================================================================
+
+struct PairState {
+    Batcher bt;
+    int n_species = 0, nkeys = 0, nbins = 0;
+    bool has_rdf = false, has_cn = false, smem_hist = false;
+    double rmax = 0.0;
+    double *d_edge2 = nullptr, *d_cnthr2 = nullptr;
+    uint16_t *d_keyidx = nullptr;
+    unsigned long long *d_slabs = nullptr, *d_hist = nullptr;
+    int grid = 0;
+    size_t smem = 0;
+    double r2search = 0.0, r2max = 0.0;
+    float inv_dr_f = 0.f;
+};
+
+static void pair_release(amofb_ctx *ctx) {
+    PairState *p = ctx->pair;
+    if (!p) return;
+    cudaStreamSynchronize(ctx->s_copy);
+    cudaStreamSynchronize(ctx->s_compute);
+    batcher_release(p->bt);
+    cudaFree(p->d_edge2); cudaFree(p->d_cnthr2); cudaFree(p->d_keyidx); cudaFree(p->d_slabs); cudaFree(p->d_hist);
+    delete p;
+    ctx->pair = nullptr;
+}
+
+template <bool R, bool C, bool M>
+static int pair_configure(amofb_ctx *ctx, PairState *p) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pair<R, C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair<R, C, M>, PAIR_TILE, p->smem));
+    if (per_sm < 1) return amofb_fail(ctx, AMOFB_ERR_CUDA, "pair kernel does not fit on an SM (smem %zu)", p->smem);
+    int force = env_int("AMOFB_PAIR_BLOCKS_PER_SM", 0);
+    if (force > 0 && force < per_sm) per_sm = force;
+    p->grid = ctx->num_sms * per_sm;
+    return AMOFB_OK;
+}
+
+template <bool R, bool C, bool M>
+static void pair_launch(amofb_ctx *ctx, PairState *p, const PairArgs &a, int grid) {
+    k_pair<R, C, M><<<grid, PAIR_TILE, p->smem, ctx->s_compute>>>(a);
+}
+
+extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, double rmax,
+                                int nbins, const double *cn_cutoff) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pair) return amofb_fail(ctx, AMOFB_ERR_STATE, "pair analysis already open; call amofb_pair_finish first");
+    if (n_atoms < 0 || n_species < 1 || n_species > AMOFB_MAX_SPECIES || (n_atoms > 0 && !species))
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "bad n_atoms/n_species (n_species must be 1..%d)", AMOFB_MAX_SPECIES);
+    if (nbins < 0 || (nbins > 0 && !(rmax > 0.0 && isfinite(rmax))))
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "nbins > 0 needs a finite rmax > 0");
+    if (nbins == 0 && !cn_cutoff) return amofb_fail(ctx, AMOFB_ERR_ARG, "nothing to compute: nbins == 0 and no cutoffs");
+    for (int i = 0; i < n_atoms; ++i)
+        if (species[i] >= n_species) return amofb_fail(ctx, AMOFB_ERR_ARG, "species[%d] = %d out of range", i, species[i]);
+    const int S = n_species;
+    double cut_max = 0.0;
+    if (cn_cutoff) {
+        for (int a = 0; a < S; ++a)
+            for (int b = 0; b < S; ++b) {
+                double c = cn_cutoff[a * S + b];
+                if (!(c >= 0.0) || !isfinite(c)) return amofb_fail(ctx, AMOFB_ERR_ARG, "cutoff[%d][%d] must be finite and >= 0", a, b);
+                if (c != cn_cutoff[b * S + a]) return amofb_fail(ctx, AMOFB_ERR_ARG, "cutoff matrix must be symmetric");
+                cut_max = std::max(cut_max, c);
+            }
+    }
+    PairState *p = new (std::nothrow) PairState();
+    if (!p) return AMOFB_ERR_MEMORY;
+    ctx->pair = p;
+    p->n_species = S;
+    p->nkeys = S * (S + 1) / 2;
+    p->nbins = nbins;
+    p->has_rdf = nbins > 0;
+    p->has_cn = cn_cutoff != nullptr;
+    p->rmax = rmax;
+
+    // exact thresholds in d2 (P4, P5)
+    std::vector<double> edge2((size_t)nbins + 1, 0.0), cnthr((size_t)p->nkeys, 0.0);
+    if (p->has_rdf) {
+        const double dr = rmax / (double)nbins;
+        for (int b = 1; b <= nbins; ++b) {
+            const double fb = (double)b;
+            double guess = (fb * dr) * (fb * dr);
+            edge2[b] = host_threshold(guess, [&](double t) { return sqrt(t) / dr >= fb; });
+        }
+        p->r2max = edge2[nbins];
+        p->inv_dr_f = (float)((double)nbins / rmax);
+    }
+    if (p->has_cn)
+        for (int a = 0; a < S; ++a)
+            for (int b = a; b < S; ++b) {
+                double c = cn_cutoff[a * S + b];
+                cnthr[fold_key(a, b, S)] = c > 0.0 ? host_threshold(c * c, [&](double t) { return sqrt(t) >= c; }) : 0.0;
+            }
+    p->r2search = p->r2max;
+    for (double t : cnthr) p->r2search = std::max(p->r2search, t);
+    std::vector<uint16_t> keyidx((size_t)S * S);
+    for (int a = 0; a < S; ++a)
+        for (int b = 0; b < S; ++b) keyidx[a * S + b] = (uint16_t)fold_key(a, b, S);
+
+    int rc = AMOFB_OK;
+    auto fail = [&](int code) { pair_release(ctx); return code; };
+    double rcut = std::max(p->has_rdf ? rmax : 0.0, cut_max);
+    if (!(rcut > 0.0)) rcut = 1e-3;   // all cutoffs zero: nothing will be counted, any grid works
+    int cell_div = env_int("AMOFB_CELL_DIV", p->has_rdf ? 2 : 1);
+    if (cell_div < 1) cell_div = 1;
+    if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, p->has_cn ? p->nkeys : 0))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_edge2, edge2.size()))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_keyidx, keyidx.size()))) return fail(rc);
+    cudaMemcpy(p->d_edge2, edge2.data(), sizeof(double) * edge2.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_cnthr2, cnthr.data(), sizeof(double) * cnthr.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_keyidx, keyidx.data(), sizeof(uint16_t) * keyidx.size(), cudaMemcpyHostToDevice);
+
+    const size_t hist_n = (size_t)p->nkeys * nbins;
+    size_t smem_full = sizeof(double) * ((size_t)nbins + 1) + sizeof(double) * p->nkeys + sizeof(uint32_t) * hist_n +
+                       sizeof(uint32_t) * p->nkeys + sizeof(uint16_t) * S * S + 16;
+    size_t smem_lite = sizeof(double) * p->nkeys + sizeof(uint32_t) * p->nkeys + sizeof(uint16_t) * S * S + 16;
+    size_t budget = (size_t)ctx->max_smem_optin > 2048 ? (size_t)ctx->max_smem_optin - 2048 : 0;
+    p->smem_hist = p->has_rdf && smem_full <= budget && !env_int("AMOFB_FORCE_GLOBAL_HIST", 0);
+    p->smem = (p->smem_hist ? smem_full : smem_lite);
+    if (p->has_rdf && p->has_cn) rc = p->smem_hist ? pair_configure<true, true, true>(ctx, p) : pair_configure<true, true, false>(ctx, p);
+    else if (p->has_rdf) rc = p->smem_hist ? pair_configure<true, false, true>(ctx, p) : pair_configure<true, false, false>(ctx, p);
+    else rc = pair_configure<false, true, false>(ctx, p);
+    if (rc) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_hist, hist_n))) return fail(rc);
+    cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * std::max<size_t>(hist_n, 1));
+    if (p->smem_hist) {
+        if ((rc = dev_alloc(ctx, &p->d_slabs, hist_n * p->grid))) return fail(rc);
+        cudaMemset(p->d_slabs, 0, sizeof(unsigned long long) * hist_n * p->grid);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { amofb_fail(ctx, AMOFB_ERR_CUDA, "pair_begin: %s", cudaGetErrorString(e)); return fail(AMOFB_ERR_CUDA); }
+    return AMOFB_OK;
+}
+
+static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool on_device, const double *cell) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    PairState *p = ctx->pair;
+    if (!p) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_pair_push before amofb_pair_begin");
+    if (n_frames < 0 || (n_frames > 0 && (!cell || (!pos && p->bt.n_atoms > 0))))
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "bad push arguments");
+    Batcher &b = p->bt;
+    for (int done = 0; done < n_frames;) {
+        int nf = std::min(b.cap_frames, n_frames - done);
+        BatchSlot *s = nullptr;
+        const double *raw = nullptr;
+        AMOFB_TRY(batcher_stage(ctx, b, nf, pos + 3 * (size_t)done * b.n_atoms, on_device, cell + 9 * (size_t)done, &s, &raw));
+        PairArgs a;
+        a.sorted = s->d_sorted; a.geom = s->d_geom; a.cell_start = s->d_cell_start;
+        a.edge2 = p->d_edge2; a.cn_thr2 = p->d_cnthr2; a.keyidx = p->d_keyidx;
+        a.slabs = p->d_slabs; a.ghist = p->d_hist; a.cn_out = s->d_out;
+        a.r2search = p->r2search; a.r2max = p->r2max; a.inv_dr_f = p->inv_dr_f;
+        a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys; a.nbins = p->nbins;
+        a.tiles_per_frame = (b.n_atoms + PAIR_TILE - 1) / PAIR_TILE;
+        long long tiles = (long long)nf * a.tiles_per_frame;
+        if (tiles > 0) {
+            // smem-histogram mode always launches the full grid: every block owns a slab
+            int grid = p->smem_hist ? p->grid : (int)std::min<long long>(tiles, p->grid);
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (ctx->profiling) {
+                CUDA_TRY(ctx, cudaEventCreate(&e0));
+                CUDA_TRY(ctx, cudaEventCreate(&e1));
+                CUDA_TRY(ctx, cudaEventRecord(e0, ctx->s_compute));
+            }
+            if (p->has_rdf && p->has_cn) { if (p->smem_hist) pair_launch<true, true, true>(ctx, p, a, grid); else pair_launch<true, true, false>(ctx, p, a, grid); }
+            else if (p->has_rdf) { if (p->smem_hist) pair_launch<true, false, true>(ctx, p, a, grid); else pair_launch<true, false, false>(ctx, p, a, grid); }
+            else pair_launch<false, true, false>(ctx, p, a, grid);
+            ctx->launches += 1;
+            CUDA_TRY(ctx, cudaGetLastError());
+            if (ctx->profiling) {
+                CUDA_TRY(ctx, cudaEventRecord(e1, ctx->s_compute));
+                ctx->pending_pair_events.emplace_back(e0, e1);
+            }
+        }
+        AMOFB_TRY(batcher_commit(ctx, b, *s, nf));
+        done += nf;
+    }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_pair_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell) {
+    return pair_push_impl(ctx, n_frames, pos, false, cell);
+}
+extern "C" int amofb_pair_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell) {
+    return pair_push_impl(ctx, n_frames, pos_device, true, cell);
+}
+
+extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
+                                 int64_t *n_frames_out, double *volume_sum_out) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    PairState *p = ctx->pair;
+    if (!p) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_pair_finish before amofb_pair_begin");
+    int rc = AMOFB_OK;
+    auto body = [&]() -> int {
+        Batcher &b = p->bt;
+        AMOFB_TRY(batcher_drain(ctx, b));
+        const int S = p->n_species;
+        if (cn_counts) {
+            if (!p->has_cn) return amofb_fail(ctx, AMOFB_ERR_ARG, "cn_counts requested but no cutoffs were given at begin");
+            if (cn_frames != b.frames_seen)
+                return amofb_fail(ctx, AMOFB_ERR_ARG, "cn_frames = %lld but %lld frames were pushed", (long long)cn_frames, (long long)b.frames_seen);
+            for (int64_t f = 0; f < b.frames_seen; ++f)
+                for (int x = 0; x < S; ++x)
+                    for (int y = 0; y < S; ++y) {
+                        unsigned long long u = b.out_all[(size_t)f * p->nkeys + fold_key(x, y, S)];
+                        cn_counts[((size_t)f * S + x) * S + y] = x == y ? 2 * u : u;
+                    }
+        }
+        if (hist) {
+            if (!p->has_rdf) return amofb_fail(ctx, AMOFB_ERR_ARG, "hist requested but nbins was 0 at begin");
+            const size_t hist_n = (size_t)p->nkeys * p->nbins;
+            if (p->smem_hist) {
+                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, p->grid, (int)hist_n, p->d_hist);
+                ctx->launches += 1;
+                CUDA_TRY(ctx, cudaGetLastError());
+            }
+            std::vector<unsigned long long> u(hist_n);
+            CUDA_TRY(ctx, cudaMemcpyAsync(u.data(), p->d_hist, sizeof(unsigned long long) * hist_n, cudaMemcpyDeviceToHost, ctx->s_compute));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+            for (int x = 0; x < S; ++x)
+                for (int y = 0; y < S; ++y) {
+                    const unsigned long long *src = u.data() + (size_t)fold_key(x, y, S) * p->nbins;
+                    uint64_t *dst = hist + ((size_t)x * S + y) * p->nbins;
+                    for (int k = 0; k < p->nbins; ++k) dst[k] = x == y ? 2 * src[k] : src[k];
+                }
+        }
+        if (n_frames_out) *n_frames_out = b.frames_seen;
+        if (volume_sum_out) *volume_sum_out = b.volume_sum;
+        return AMOFB_OK;
+    };
+    rc = body();
+    if (ctx->profiling) drain_pair_events(ctx);
+    pair_release(ctx);
+    return rc;
+}
+
+extern "C" int amofb_rdf_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, double rmax, int nbins) {
+    if (ctx && nbins < 1) return amofb_fail(ctx, AMOFB_ERR_ARG, "amofb_rdf_begin needs nbins >= 1");
+    return amofb_pair_begin(ctx, n_atoms, n_species, species, rmax, nbins, nullptr);
+}
+extern "C" int amofb_rdf_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell) {
+    return amofb_pair_push(ctx, n_frames, pos, cell);
+}
+extern "C" int amofb_rdf_finish(amofb_ctx *ctx, uint64_t *hist, int64_t *n_frames_out, double *volume_sum_out) {
+    return amofb_pair_finish(ctx, hist, nullptr, 0, n_frames_out, volume_sum_out);
+}
+extern "C" int amofb_cn_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, const double *cn_cutoff) {
+    if (ctx && !cn_cutoff) return amofb_fail(ctx, AMOFB_ERR_ARG, "amofb_cn_begin needs a cutoff matrix");
+    return amofb_pair_begin(ctx, n_atoms, n_species, species, 0.0, 0, cn_cutoff);
+}
+extern "C" int amofb_cn_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell) {
+    return amofb_pair_push(ctx, n_frames, pos, cell);
+}
+extern "C" int amofb_cn_finish(amofb_ctx *ctx, uint64_t *cn_counts, int64_t cn_frames) {
+    return amofb_pair_finish(ctx, nullptr, cn_counts, cn_frames, nullptr, nullptr);
+}
+
+#include "bad_host.inl"
+#include "msd_host.inl"

@@ -1,0 +1,123 @@
+// bad.cuh -- bond-angle triplet kernel (K4 of SURVEY.md 2.1).
+//
+// One thread owns one centre atom of the cell-sorted frame: it walks the FULL stencil, keeps the unit vectors of
+// every neighbour under the pair cutoffs (P5), then for each requested (A, B) triple enumerates the unordered
+// pairs of its B-neighbours.  The angle itself is never formed on the device: x = u_p . u_q is computed in fp64
+// in the oracle's operation order (P6) and located in a table of thresholds on -x that the host bisected with its
+// own libm acos and the np.histogram edge rule (P7), so the bin is the one the CPU path takes, bit for bit,
+// without depending on CUDA's acos.
+#pragma once
+#include "prep.cuh"
+
+#define BAD_NB_MAX 64        // neighbours of any species kept per centre
+#define BAD_MAX_TRIPLES 64
+
+struct BadArgs {
+    const SAtom *sorted;
+    const FrameGeom *geom;
+    const uint32_t *cell_start;
+    const double *cn_thr2;        // [nkeys]
+    const uint16_t *keyidx;       // [S*S]
+    const int2 *triples;          // [n_triples] (A, B), -1 = any
+    const double *tthr;           // [nbins+2]: tthr[0] = -2, tthr[k] = smallest -x in bin >= k, tthr[nbins+1] = +2
+    unsigned long long *hist;     // [n_triples][AMOFB_BAD_MAX_CN+1][nbins]
+    unsigned long long *dropped;  // [n_triples]
+    int *flags;                   // bit 0: neighbour overflow, bit 1: cn > AMOFB_BAD_MAX_CN
+    unsigned long long centre_mask[AMOFB_MAX_SPECIES];   // triples whose A matches this species
+    double r2search;
+    float inv_dtheta_f;
+    int n_atoms, n_frames, n_species, nkeys, n_triples, nbins;
+};
+
+// index K in [0, nbins] of t = -x: K < nbins is the histogram bin, K == nbins means "beyond the last edge"
+__device__ __forceinline__ int bad_bin(double t, const double *__restrict__ tthr, float inv_dtheta_f, int nbins) {
+    float xf = fminf(fmaxf((float)(-t), -1.0f), 1.0f);
+    int k = (int)(acosf(xf) * 57.29577951308232f * inv_dtheta_f);
+    k = k < 0 ? 0 : (k > nbins ? nbins : k);
+    while (t < __ldg(tthr + k)) --k;          // tthr[0] = -2 stops it
+    while (t >= __ldg(tthr + k + 1)) ++k;     // tthr[nbins+1] = +2 stops it
+    return k;
+}
+
+__global__ void __launch_bounds__(128) k_bad(BadArgs a) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= (long long)a.n_frames * a.n_atoms) return;
+    const int f = (int)(g / a.n_atoms);
+    const int i = (int)(g - (long long)f * a.n_atoms);
+    const SAtom *fr = a.sorted + (long long)f * a.n_atoms;
+    const SAtom me = load_satom(fr + i);
+    const int si = (int)(me.s & 0xff);
+    const unsigned long long mine = a.centre_mask[si];
+    if (!mine) return;
+    const FrameGeom &G = a.geom[f];
+    const uint32_t *cs = a.cell_start + G.cs_off;
+    const int S = a.n_species;
+    const int c0 = (int)((me.s >> 8) & 0xfff), c1 = (int)((me.s >> 20) & 0xfff), c2 = (int)((me.s >> 32) & 0xfff);
+    const int nc0 = G.nc[0], nc1 = G.nc[1], nc2 = G.nc[2];
+    const int m0 = G.m[0], m1 = G.m[1], m2 = G.m[2];
+
+    double ux[BAD_NB_MAX], uy[BAD_NB_MAX], uz[BAD_NB_MAX];
+    unsigned char sp[BAD_NB_MAX];
+    int nn = 0;
+    bool overflow = false;
+    for (int d0 = -m0; d0 <= m0; ++d0) {
+        const int t0 = c0 + d0, s0 = floordiv_i(t0, nc0), q0 = t0 - s0 * nc0;
+        for (int d1 = -m1; d1 <= m1; ++d1) {
+            const int t1 = c1 + d1, s1 = floordiv_i(t1, nc1), q1 = t1 - s1 * nc1;
+            const int rowbase = (q0 * nc1 + q1) * nc2;
+            int d2 = -m2;
+            while (d2 <= m2) {
+                const int t2 = c2 + d2, s2 = floordiv_i(t2, nc2), q2 = t2 - s2 * nc2;
+                const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
+                const int jb = (int)cs[rowbase + q2], je = (int)cs[rowbase + q2 + len];
+                const bool self_image = (s0 == 0 && s1 == 0 && s2 == 0);
+                const double fs0 = (double)s0, fs1 = (double)s1, fs2 = (double)s2;
+                const double Tx = (fs0 * G.cell[0] + fs1 * G.cell[3]) + fs2 * G.cell[6];
+                const double Ty = (fs0 * G.cell[1] + fs1 * G.cell[4]) + fs2 * G.cell[7];
+                const double Tz = (fs0 * G.cell[2] + fs1 * G.cell[5]) + fs2 * G.cell[8];
+                for (int j = jb; j < je; ++j) {
+                    if (self_image && j == i) continue;
+                    const SAtom o = load_satom(fr + j);
+                    const double dx = (o.x - me.x) + Tx;
+                    const double dy = (o.y - me.y) + Ty;
+                    const double dz = (o.z - me.z) + Tz;
+                    const double dd = (dx * dx + dy * dy) + dz * dz;
+                    if (dd < a.r2search) {
+                        const int sj = (int)(o.s & 0xff);
+                        if (dd < __ldg(a.cn_thr2 + a.keyidx[si * S + sj])) {
+                            if (nn < BAD_NB_MAX) {
+                                const double n = sqrt(dd);          // P6: u = v / |v|, componentwise
+                                ux[nn] = dx / n; uy[nn] = dy / n; uz[nn] = dz / n;
+                                sp[nn] = (unsigned char)sj;
+                                ++nn;
+                            } else overflow = true;
+                        }
+                    }
+                }
+                d2 += len;
+            }
+        }
+    }
+    if (overflow) { atomicOr(a.flags, 1); return; }
+    if (nn < 2) return;
+    for (int t = 0; t < a.n_triples; ++t) {
+        if (!((mine >> t) & 1ull)) continue;
+        const int B = a.triples[t].y;
+        int cn = 0;
+        for (int p = 0; p < nn; ++p) cn += (B < 0 || sp[p] == B);
+        if (cn < 2) continue;
+        if (cn > AMOFB_BAD_MAX_CN) { atomicOr(a.flags, 2); continue; }
+        unsigned long long *row = a.hist + ((size_t)t * (AMOFB_BAD_MAX_CN + 1) + cn) * a.nbins;
+        for (int p = 0; p < nn; ++p) {
+            if (!(B < 0 || sp[p] == B)) continue;
+            for (int q = p + 1; q < nn; ++q) {
+                if (!(B < 0 || sp[q] == B)) continue;
+                const double x = (ux[p] * ux[q] + uy[p] * uy[q]) + uz[p] * uz[q];
+                if (!(fabs(x) <= 1.0)) { atomicAdd(a.dropped + t, 1ull); continue; }   // acos -> NaN, np.histogram drops it
+                const int k = bad_bin(-x, a.tthr, a.inv_dtheta_f, a.nbins);
+                if (k >= a.nbins) atomicAdd(a.dropped + t, 1ull);
+                else atomicAdd(row + k, 1ull);
+            }
+        }
+    }
+}

@@ -1,0 +1,225 @@
+// bad_host.inl -- host side of the bond-angle analysis (included by amofb.cu)
+
+struct BadState {
+    Batcher bt;
+    int n_species = 0, nkeys = 0, n_triples = 0, nbins = 0;
+    double dtheta = 0.0, rcut = 0.0, r2search = 0.0;
+    double *d_cnthr2 = nullptr, *d_tthr = nullptr;
+    uint16_t *d_keyidx = nullptr;
+    int2 *d_triples = nullptr;
+    unsigned long long *d_hist = nullptr, *d_dropped = nullptr;
+    int *d_flags = nullptr;
+    unsigned long long centre_mask[AMOFB_MAX_SPECIES];
+};
+
+static void bad_release(amofb_ctx *ctx) {
+    BadState *p = ctx->bad;
+    if (!p) return;
+    cudaStreamSynchronize(ctx->s_copy);
+    cudaStreamSynchronize(ctx->s_compute);
+    batcher_release(p->bt);
+    cudaFree(p->d_cnthr2); cudaFree(p->d_tthr); cudaFree(p->d_keyidx); cudaFree(p->d_triples);
+    cudaFree(p->d_hist); cudaFree(p->d_dropped); cudaFree(p->d_flags);
+    delete p;
+    ctx->bad = nullptr;
+}
+
+// P7: np.histogram(theta, bins=edges) with edges e_k = k*dtheta, k = 0..nbins.
+// Returns the bin, nbins for "above the last edge" (dropped), never called with NaN.
+static inline int host_theta_index(double theta, double dtheta, int nbins) {
+    const double last = (double)nbins * dtheta;
+    if (theta > last) return nbins;
+    if (theta == last) return nbins - 1;          // the last bin is closed on the right
+    if (theta < 0.0) return 0;
+    long k = (long)(theta / dtheta);
+    if (k > nbins - 1) k = nbins - 1;
+    while (k > 0 && theta < (double)k * dtheta) --k;                  // settle on e_k <= theta < e_{k+1}
+    while (k < nbins - 1 && theta >= (double)(k + 1) * dtheta) ++k;
+    return (int)k;
+}
+
+// order-preserving map double -> uint64 over the whole real line
+static inline uint64_t dbl_key(double d) {
+    uint64_t u;
+    memcpy(&u, &d, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+static inline double key_dbl(uint64_t k) {
+    uint64_t u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+}
+
+// tthr[k], k = 1..nbins: smallest t = -x in [-1, 1] whose angle acos(-t)*(180/pi) (P6, host libm) falls in
+// bin >= k; 2.0 when no t does.  tthr[0] = -2, tthr[nbins+1] = +2 are sentinels.
+static void host_angle_thresholds(double dtheta, int nbins, std::vector<double> &tthr) {
+    const double deg = 180.0 / 3.14159265358979323846;
+    tthr.assign((size_t)nbins + 2, 2.0);
+    tthr[0] = -2.0;
+    auto index_of = [&](double t) { return host_theta_index(acos(-t) * deg, dtheta, nbins); };
+    const uint64_t klo = dbl_key(-1.0), khi = dbl_key(1.0);
+    const int top = index_of(1.0);
+    uint64_t prev = klo;   // thresholds are non-decreasing: start each bisection at the previous one
+    for (int k = 1; k <= nbins; ++k) {
+        if (top < k) break;                       // unreachable bins keep the +2 sentinel
+        if (index_of(key_dbl(prev)) >= k) { tthr[k] = key_dbl(prev); continue; }
+        uint64_t lo = prev, hi = khi;             // index(lo) < k <= index(hi)
+        while (hi - lo > 1) {
+            uint64_t mid = lo + (hi - lo) / 2;
+            if (index_of(key_dbl(mid)) >= k) hi = mid; else lo = mid;
+        }
+        tthr[k] = key_dbl(hi);
+        prev = hi;
+    }
+}
+
+extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, const double *cutoff,
+                               int n_triples, const int *triples, double dtheta, int nbins) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->bad) return amofb_fail(ctx, AMOFB_ERR_STATE, "bond-angle analysis already open; call amofb_bad_finish first");
+    if (n_atoms < 0 || n_species < 1 || n_species > AMOFB_MAX_SPECIES || (n_atoms > 0 && !species) || !cutoff)
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "bad n_atoms/n_species/cutoff");
+    if (n_triples < 1 || n_triples > BAD_MAX_TRIPLES || !triples)
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "n_triples must be 1..%d", BAD_MAX_TRIPLES);
+    if (nbins < 1 || !(dtheta > 0.0) || !isfinite(dtheta)) return amofb_fail(ctx, AMOFB_ERR_ARG, "bad dtheta/nbins");
+    for (int i = 0; i < n_atoms; ++i)
+        if (species[i] >= n_species) return amofb_fail(ctx, AMOFB_ERR_ARG, "species[%d] = %d out of range", i, species[i]);
+    const int S = n_species;
+    double cut_max = 0.0;
+    for (int a = 0; a < S; ++a)
+        for (int b = 0; b < S; ++b) {
+            double c = cutoff[a * S + b];
+            if (!(c >= 0.0) || !isfinite(c)) return amofb_fail(ctx, AMOFB_ERR_ARG, "cutoff[%d][%d] must be finite and >= 0", a, b);
+            if (c != cutoff[b * S + a]) return amofb_fail(ctx, AMOFB_ERR_ARG, "cutoff matrix must be symmetric");
+            cut_max = std::max(cut_max, c);
+        }
+    for (int t = 0; t < n_triples; ++t)
+        for (int k = 0; k < 2; ++k)
+            if (triples[2 * t + k] < -1 || triples[2 * t + k] >= S)
+                return amofb_fail(ctx, AMOFB_ERR_ARG, "triples[%d][%d] out of range", t, k);
+    BadState *p = new (std::nothrow) BadState();
+    if (!p) return AMOFB_ERR_MEMORY;
+    ctx->bad = p;
+    p->n_species = S; p->nkeys = S * (S + 1) / 2; p->n_triples = n_triples; p->nbins = nbins; p->dtheta = dtheta;
+    p->rcut = cut_max;
+    std::vector<double> cnthr((size_t)p->nkeys, 0.0), tthr;
+    for (int a = 0; a < S; ++a)
+        for (int b = a; b < S; ++b) {
+            double c = cutoff[a * S + b];
+            cnthr[fold_key(a, b, S)] = c > 0.0 ? host_threshold(c * c, [&](double t) { return sqrt(t) >= c; }) : 0.0;
+        }
+    p->r2search = 0.0;
+    for (double t : cnthr) p->r2search = std::max(p->r2search, t);
+    host_angle_thresholds(dtheta, nbins, tthr);
+    std::vector<uint16_t> keyidx((size_t)S * S);
+    for (int a = 0; a < S; ++a)
+        for (int b = 0; b < S; ++b) keyidx[a * S + b] = (uint16_t)fold_key(a, b, S);
+    std::vector<int2> tr((size_t)n_triples);
+    memset(p->centre_mask, 0, sizeof p->centre_mask);
+    for (int t = 0; t < n_triples; ++t) {
+        tr[t] = make_int2(triples[2 * t], triples[2 * t + 1]);
+        for (int s = 0; s < S; ++s)
+            if (tr[t].x < 0 || tr[t].x == s) p->centre_mask[s] |= 1ull << t;
+    }
+    int rc = AMOFB_OK;
+    auto fail = [&](int code) { bad_release(ctx); return code; };
+    double rcut = cut_max > 0.0 ? cut_max : 1e-3;
+    int cell_div = env_int("AMOFB_BAD_CELL_DIV", 1);
+    if (cell_div < 1) cell_div = 1;
+    if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, 0))) return fail(rc);
+    const size_t hist_n = (size_t)n_triples * (AMOFB_BAD_MAX_CN + 1) * nbins;
+    if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_tthr, tthr.size()))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_keyidx, keyidx.size()))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_triples, tr.size()))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_hist, hist_n))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_dropped, (size_t)n_triples))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_flags, 1))) return fail(rc);
+    cudaMemcpy(p->d_cnthr2, cnthr.data(), sizeof(double) * cnthr.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_tthr, tthr.data(), sizeof(double) * tthr.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_keyidx, keyidx.data(), sizeof(uint16_t) * keyidx.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_triples, tr.data(), sizeof(int2) * tr.size(), cudaMemcpyHostToDevice);
+    cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * hist_n);
+    cudaMemset(p->d_dropped, 0, sizeof(unsigned long long) * n_triples);
+    cudaMemset(p->d_flags, 0, sizeof(int));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { amofb_fail(ctx, AMOFB_ERR_CUDA, "bad_begin: %s", cudaGetErrorString(e)); return fail(AMOFB_ERR_CUDA); }
+    return AMOFB_OK;
+}
+
+static int bad_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool on_device, const double *cell) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    BadState *p = ctx->bad;
+    if (!p) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_bad_push before amofb_bad_begin");
+    if (n_frames < 0 || (n_frames > 0 && (!cell || (!pos && p->bt.n_atoms > 0))))
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "bad push arguments");
+    Batcher &b = p->bt;
+    // P6 precondition: the neighbour image vector is the minimum image only below half the smallest height
+    if (p->rcut > 0.0)
+        for (int f = 0; f < n_frames; ++f) {
+            double inv[9], h[3];
+            if (!host_cell_inverse(cell + 9 * (size_t)f, inv))
+                return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %lld: singular cell", (long long)(b.frames_seen + f));
+            host_cell_heights(inv, h);
+            for (int k = 0; k < 3; ++k)
+                if (!(p->rcut < 0.5 * h[k]))
+                    return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %lld: cutoff %g is not below half the cell height %g",
+                                      (long long)(b.frames_seen + f), p->rcut, h[k]);
+        }
+    for (int done = 0; done < n_frames;) {
+        int nf = std::min(b.cap_frames, n_frames - done);
+        BatchSlot *s = nullptr;
+        const double *raw = nullptr;
+        AMOFB_TRY(batcher_stage(ctx, b, nf, pos + 3 * (size_t)done * b.n_atoms, on_device, cell + 9 * (size_t)done, &s, &raw));
+        BadArgs a;
+        a.sorted = s->d_sorted; a.geom = s->d_geom; a.cell_start = s->d_cell_start;
+        a.cn_thr2 = p->d_cnthr2; a.keyidx = p->d_keyidx; a.triples = p->d_triples; a.tthr = p->d_tthr;
+        a.hist = p->d_hist; a.dropped = p->d_dropped; a.flags = p->d_flags;
+        memcpy(a.centre_mask, p->centre_mask, sizeof a.centre_mask);
+        a.r2search = p->r2search; a.inv_dtheta_f = (float)(1.0 / p->dtheta);
+        a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys;
+        a.n_triples = p->n_triples; a.nbins = p->nbins;
+        long long total = (long long)nf * b.n_atoms;
+        if (total > 0) {
+            k_bad<<<(unsigned)((total + 127) / 128), 128, 0, ctx->s_compute>>>(a);
+            ctx->launches += 1;
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        AMOFB_TRY(batcher_commit(ctx, b, *s, nf));
+        done += nf;
+    }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_bad_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell) {
+    return bad_push_impl(ctx, n_frames, pos, false, cell);
+}
+extern "C" int amofb_bad_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell) {
+    return bad_push_impl(ctx, n_frames, pos_device, true, cell);
+}
+
+extern "C" int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *dropped, int64_t *n_frames_out) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    BadState *p = ctx->bad;
+    if (!p) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_bad_finish before amofb_bad_begin");
+    auto body = [&]() -> int {
+        AMOFB_TRY(batcher_drain(ctx, p->bt));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+        int flags = 0;
+        CUDA_TRY(ctx, cudaMemcpy(&flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flags & 1) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "a centre has more than %d neighbours under the cutoffs", BAD_NB_MAX);
+        if (flags & 2) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "a centre has more than %d B-neighbours", AMOFB_BAD_MAX_CN);
+        const size_t hist_n = (size_t)p->n_triples * (AMOFB_BAD_MAX_CN + 1) * p->nbins;
+        if (hist) CUDA_TRY(ctx, cudaMemcpy(hist, p->d_hist, sizeof(uint64_t) * hist_n, cudaMemcpyDeviceToHost));
+        if (dropped) CUDA_TRY(ctx, cudaMemcpy(dropped, p->d_dropped, sizeof(uint64_t) * p->n_triples, cudaMemcpyDeviceToHost));
+        if (n_frames_out) *n_frames_out = p->bt.frames_seen;
+        return AMOFB_OK;
+    };
+    int rc = body();
+    bad_release(ctx);
+    return rc;
+}

@@ -1,0 +1,186 @@
+// common.cuh -- context, error plumbing and the pinned host-side geometry of libamofb.
+//
+// Host-side fp64 arithmetic here is bin-deciding (inverse cell, image shifts, bin thresholds), so
+// this translation unit is compiled with -Xcompiler -ffp-contract=off and the device code with
+// -fmad=false: every expression below is evaluated operation by operation in IEEE-754 binary64,
+// in the order written, and mirrors pins P1-P8 of oracle/amof_oracle.c.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/amofb.h"
+
+#define AMOFB_VERSION_STRING "amofb 0.1 (sm_100a)"
+
+struct PairState;
+struct BadState;
+struct MsdState;
+
+struct amofb_ctx {
+    int device = 0;
+    cudaStream_t s_compute = nullptr;
+    cudaStream_t s_copy = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    bool profiling = false;
+    double pair_ms = 0.0;
+    int64_t pair_launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_pair_events;
+    PairState *pair = nullptr;
+    BadState *bad = nullptr;
+    MsdState *msd = nullptr;
+};
+
+static int amofb_fail(amofb_ctx *ctx, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+static int amofb_fail(amofb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return amofb_fail((ctx), AMOFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                              __FILE__, __LINE__);                                                       \
+    } while (0)
+
+#define AMOFB_TRY(expr)            \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != AMOFB_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Per-frame geometry, computed on the host and uploaded with every batch.
+struct FrameGeom {
+    double cell[9];   // rows = lattice vectors
+    double inv[9];    // P1
+    int nc[3];        // linked cells per axis
+    int m[3];         // stencil half-width per axis (cells)
+    int ncell;        // nc0*nc1*nc2
+    int cs_off;       // offset of this frame's cell_start array (ncell+1 entries) in the batch-wide array
+    int frame_id;     // global frame index (for per-frame outputs)
+    int pad_;
+};
+
+// P1: inverse by cofactors over the determinant, fractional coordinate f = p . inv
+static inline bool host_cell_inverse(const double *c, double *inv) {
+    double m00 = c[4] * c[8] - c[5] * c[7];
+    double m01 = c[3] * c[8] - c[5] * c[6];
+    double m02 = c[3] * c[7] - c[4] * c[6];
+    double det = (c[0] * m00 - c[1] * m01) + c[2] * m02;
+    if (!(det != 0.0) || !isfinite(det)) return false;
+    inv[0] = m00 / det;
+    inv[1] = (c[2] * c[7] - c[1] * c[8]) / det;
+    inv[2] = (c[1] * c[5] - c[2] * c[4]) / det;
+    inv[3] = (c[5] * c[6] - c[3] * c[8]) / det;
+    inv[4] = (c[0] * c[8] - c[2] * c[6]) / det;
+    inv[5] = (c[2] * c[3] - c[0] * c[5]) / det;
+    inv[6] = m02 / det;
+    inv[7] = (c[1] * c[6] - c[0] * c[7]) / det;
+    inv[8] = (c[0] * c[4] - c[1] * c[3]) / det;
+    for (int k = 0; k < 9; ++k)
+        if (!isfinite(inv[k])) return false;
+    return true;
+}
+
+static inline double host_cell_volume(const double *c) {
+    double m00 = c[4] * c[8] - c[5] * c[7];
+    double m01 = c[3] * c[8] - c[5] * c[6];
+    double m02 = c[3] * c[7] - c[4] * c[6];
+    return fabs((c[0] * m00 - c[1] * m01) + c[2] * m02);
+}
+
+// perpendicular heights: h_k = 1/|column k of inv|
+static inline void host_cell_heights(const double *inv, double *h) {
+    for (int k = 0; k < 3; ++k) {
+        double s = (inv[0 + k] * inv[0 + k] + inv[3 + k] * inv[3 + k]) + inv[6 + k] * inv[6 + k];
+        h[k] = 1.0 / sqrt(s);
+    }
+}
+
+// Fill the linked-cell grid of one frame for a search radius rcut.
+//   cells of width >= rcut*(1+1e-9)/cell_div along every perpendicular direction, so a stencil of
+//   half-width m_k = ceil(rcut*(1+1e-9)/w_k) cells provably covers every pair within rcut even though
+//   atoms sit in their cell only up to fp rounding.
+static inline bool host_fill_geom(FrameGeom &g, const double *cell, double rcut, int cell_div, int n_atoms) {
+    memcpy(g.cell, cell, sizeof(double) * 9);
+    if (!host_cell_inverse(cell, g.inv)) return false;
+    double h[3];
+    host_cell_heights(g.inv, h);
+    double rpad = rcut * (1.0 + 1e-9) + 1e-300;
+    double total = 1.0;
+    for (int k = 0; k < 3; ++k) {
+        double n = floor(h[k] * cell_div / rpad);
+        if (!(n >= 1.0)) n = 1.0;
+        if (n > 1024.0) n = 1024.0;
+        g.nc[k] = (int)n;
+        total *= n;
+    }
+    // keep the grid from exploding on sparse boxes: at most ~4 cells per atom (+64)
+    double cap = 4.0 * (double)n_atoms + 64.0;
+    if (total > cap) {
+        double s = cbrt(cap / total);
+        for (int k = 0; k < 3; ++k) {
+            int n = (int)floor(g.nc[k] * s);
+            g.nc[k] = n < 1 ? 1 : n;
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        double w = h[k] / g.nc[k];
+        int m = (int)ceil(rpad / w);
+        if (m < 1) m = 1;
+        if (m > 60) return false;   // box far smaller than the cutoff: refuse instead of looping forever
+        g.m[k] = m;
+    }
+    g.ncell = g.nc[0] * g.nc[1] * g.nc[2];
+    g.pad_ = 0;
+    return true;
+}
+
+// Smallest non-negative double t with pred(t) true, pred monotone (false ... false true ... true) in t.
+// Bisection on the bit pattern, which is order-preserving for non-negative doubles.
+template <typename Pred>
+static inline double host_threshold(double hi_guess, Pred pred) {
+    uint64_t lo = 0, hi;
+    double h = hi_guess;
+    if (!(h > 0.0)) h = 1e-300;
+    while (!pred(h)) h *= 2.0;
+    memcpy(&hi, &h, 8);
+    if (pred(0.0)) return 0.0;
+    // invariant: pred(lo) false, pred(hi) true
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        double t;
+        memcpy(&t, &mid, 8);
+        if (pred(t)) hi = mid; else lo = mid;
+    }
+    double t;
+    memcpy(&t, &hi, 8);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers shared by the kernels
+
+__device__ __forceinline__ int floordiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+__device__ __forceinline__ unsigned long long atomicAdd64(unsigned long long *p, unsigned long long v) {
+    return atomicAdd(p, v);
+}

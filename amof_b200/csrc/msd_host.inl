@@ -1,0 +1,309 @@
+// msd_host.inl -- host side of the mean-squared-displacement analysis (included by amofb.cu)
+
+struct MsdState {
+    int T = 0, n = 0, S = 0;
+    double *d_P = nullptr;            // [n][T][3] atom-major
+    MsdGeom *d_geom = nullptr;        // [T]
+    double *d_masses = nullptr;       // [n]
+    uint8_t *d_species = nullptr;     // [n]
+    double *d_com = nullptr;          // [T][3]
+    double *d_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    int stage_frames = 0, next_stage = 0;
+    bool have_com = false, prepared = false, consumed = false;
+    std::vector<double> cell;         // host copy [T][9]
+    double mass_sum = 0.0;
+};
+
+static void msd_release(amofb_ctx *ctx) {
+    MsdState *p = ctx->msd;
+    if (!p) return;
+    cudaStreamSynchronize(ctx->s_copy);
+    cudaStreamSynchronize(ctx->s_compute);
+    cudaFree(p->d_P); cudaFree(p->d_geom); cudaFree(p->d_masses); cudaFree(p->d_species); cudaFree(p->d_com);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->d_stage[i]);
+        if (p->ev_stage[i]) cudaEventDestroy(p->ev_stage[i]);
+    }
+    delete p;
+    ctx->msd = nullptr;
+}
+
+extern "C" int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const double *masses, const uint8_t *species,
+                               int n_species, const double *cell) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->msd) return amofb_fail(ctx, AMOFB_ERR_STATE, "MSD analysis already open; call amofb_msd_end first");
+    if (n_frames < 1 || n_atoms < 1 || n_species < 1 || n_species > AMOFB_MAX_SPECIES || !masses || !species || !cell)
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "bad MSD arguments");
+    for (int i = 0; i < n_atoms; ++i)
+        if (species[i] >= n_species) return amofb_fail(ctx, AMOFB_ERR_ARG, "species[%d] = %d out of range", i, species[i]);
+    MsdState *p = new (std::nothrow) MsdState();
+    if (!p) return AMOFB_ERR_MEMORY;
+    ctx->msd = p;
+    p->T = n_frames; p->n = n_atoms; p->S = n_species;
+    p->cell.assign(cell, cell + 9 * (size_t)n_frames);
+    std::vector<MsdGeom> geom((size_t)n_frames);
+    int rc = AMOFB_OK;
+    auto fail = [&](int code) { msd_release(ctx); return code; };
+    for (int k = 0; k < n_frames; ++k) {
+        memcpy(geom[k].cell, cell + 9 * (size_t)k, sizeof(double) * 9);
+        if (!host_cell_inverse(cell + 9 * (size_t)k, geom[k].inv)) {
+            amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %d: singular cell", k);
+            return fail(AMOFB_ERR_GEOMETRY);
+        }
+    }
+    for (int i = 0; i < n_atoms; ++i) p->mass_sum += masses[i];
+    if ((rc = dev_alloc(ctx, &p->d_P, (size_t)n_atoms * n_frames * 3))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_geom, (size_t)n_frames))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_masses, (size_t)n_atoms))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_species, (size_t)n_atoms))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_com, (size_t)n_frames * 3))) return fail(rc);
+    // staging: >= 32 frames per chunk when that stays below 1 GiB per slot, so the transpose writes long runs
+    size_t frame_bytes = sizeof(double) * 3 * (size_t)n_atoms;
+    long long sf = (long long)((1ull << 30) / frame_bytes);
+    p->stage_frames = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(sf, 256), n_frames));
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = dev_alloc(ctx, &p->d_stage[i], (size_t)p->stage_frames * n_atoms * 3))) return fail(rc);
+        cudaEventCreateWithFlags(&p->ev_stage[i], cudaEventDisableTiming);
+    }
+    cudaMemcpy(p->d_geom, geom.data(), sizeof(MsdGeom) * geom.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_masses, masses, sizeof(double) * n_atoms, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_species, species, (size_t)n_atoms, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { amofb_fail(ctx, AMOFB_ERR_CUDA, "msd_begin: %s", cudaGetErrorString(e)); return fail(AMOFB_ERR_CUDA); }
+    return AMOFB_OK;
+}
+
+static int msd_state(amofb_ctx *ctx, MsdState **out, const char *what) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->msd) return amofb_fail(ctx, AMOFB_ERR_STATE, "%s before amofb_msd_begin", what);
+    *out = ctx->msd;
+    return AMOFB_OK;
+}
+
+static void msd_transpose_launch(amofb_ctx *ctx, MsdState *p, const double *src, int first, int count) {
+    dim3 grid((p->n + 31) / 32, (count + 31) / 32);
+    k_msd_transpose<<<grid, 256, 0, ctx->s_compute>>>(src, p->d_P, p->n, p->T, first, count);
+    ctx->launches += 1;
+}
+
+static int msd_load_impl(amofb_ctx *ctx, int first_frame, int count, const double *pos, bool on_device) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_load"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_load after the positions were transformed");
+    if (first_frame < 0 || count < 0 || first_frame + (long long)count > p->T || (count > 0 && !pos))
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "frames [%d, %d) outside [0, %d)", first_frame, first_frame + count, p->T);
+    p->have_com = false;
+    const size_t fr = 3 * (size_t)p->n;
+    for (int done = 0; done < count;) {
+        int nf = std::min(p->stage_frames, count - done);
+        const double *src = pos + fr * done;
+        if (!on_device) {
+            int sl = p->next_stage;
+            p->next_stage ^= 1;
+            CUDA_TRY(ctx, cudaEventSynchronize(p->ev_stage[sl]));   // the transpose that last read this slot is done
+            CUDA_TRY(ctx, cudaMemcpyAsync(p->d_stage[sl], src, sizeof(double) * fr * nf, cudaMemcpyHostToDevice, ctx->s_copy));
+            cudaEvent_t ev;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventRecord(ev, ctx->s_copy));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_compute, ev, 0));
+            CUDA_TRY(ctx, cudaEventDestroy(ev));
+            msd_transpose_launch(ctx, p, p->d_stage[sl], first_frame + done, nf);
+            CUDA_TRY(ctx, cudaGetLastError());
+            CUDA_TRY(ctx, cudaEventRecord(p->ev_stage[sl], ctx->s_compute));
+        } else {
+            msd_transpose_launch(ctx, p, src, first_frame + done, nf);
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        done += nf;
+    }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_msd_load(amofb_ctx *ctx, int first_frame, int count, const double *pos) {
+    return msd_load_impl(ctx, first_frame, count, pos, false);
+}
+extern "C" int amofb_msd_load_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device) {
+    return msd_load_impl(ctx, first_frame, count, pos_device, true);
+}
+
+static int msd_scan_grid(amofb_ctx *ctx, int n) {
+    long long warps = n;
+    long long blocks = (warps + 7) / 8;
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)ctx->num_sms * 8));
+}
+
+extern "C" int amofb_msd_unwrap(amofb_ctx *ctx) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_unwrap"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_unwrap after the positions were transformed");
+    k_msd_scan<false><<<msd_scan_grid(ctx, p->n), 256, 0, ctx->s_compute>>>(p->d_P, p->d_geom, nullptr, p->n, p->T);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    p->have_com = false;
+    return AMOFB_OK;
+}
+
+// out[len] = per-frame sums over atoms with weights d_w, NC components
+template <int NC>
+static int msd_frame_sums(amofb_ctx *ctx, MsdState *p, const double *d_w, double *d_out) {
+    int groups = std::max(1, std::min(64, p->n / 256));
+    double *d_partial = nullptr;
+    AMOFB_TRY(dev_alloc(ctx, &d_partial, (size_t)groups * p->T * NC));
+    dim3 grid((p->T + 31) / 32, groups);
+    k_msd_frame_sums<NC><<<grid, 256, 0, ctx->s_compute>>>(p->d_P, d_w, p->n, p->T, d_partial);
+    k_msd_sum_groups<<<std::max(1, std::min((p->T * NC + 255) / 256, ctx->num_sms * 4)), 256, 0, ctx->s_compute>>>(d_partial, groups, p->T * NC, d_out);
+    ctx->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
+    cudaFree(d_partial);
+    CUDA_TRY(ctx, e);
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_msd_com_sums(amofb_ctx *ctx, double *sums) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_com_sums"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_com_sums after the positions were transformed");
+    if (!sums) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
+    AMOFB_TRY(msd_frame_sums<3>(ctx, p, p->d_masses, p->d_com));   // d_com temporarily holds the weighted sums
+    std::vector<double> tmp((size_t)p->T * 3);
+    CUDA_TRY(ctx, cudaMemcpy(tmp.data(), p->d_com, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < p->T; ++k) {
+        sums[4 * (size_t)k] = tmp[3 * (size_t)k];
+        sums[4 * (size_t)k + 1] = tmp[3 * (size_t)k + 1];
+        sums[4 * (size_t)k + 2] = tmp[3 * (size_t)k + 2];
+        sums[4 * (size_t)k + 3] = p->mass_sum;
+    }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_msd_set_com(amofb_ctx *ctx, const double *com) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_set_com"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_set_com after the positions were transformed");
+    if (!com) return amofb_fail(ctx, AMOFB_ERR_ARG, "null centre of mass");
+    CUDA_TRY(ctx, cudaMemcpy(p->d_com, com, sizeof(double) * 3 * (size_t)p->T, cudaMemcpyHostToDevice));
+    p->have_com = true;
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window, double *sums) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_window"));
+    if (p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "positions were consumed by amofb_msd_direct");
+    if (n_window < 0 || (n_window > 0 && (!window || !sums))) return amofb_fail(ctx, AMOFB_ERR_ARG, "bad window arguments");
+    if (!p->prepared) {
+        if (!p->have_com) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_window needs amofb_msd_set_com first");
+        k_msd_scan<true><<<msd_scan_grid(ctx, p->n), 256, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+        p->prepared = true;
+    }
+    if (n_window == 0) return AMOFB_OK;
+    const int S = p->S, threads = 512, nwarp = threads / 32;
+    int *d_window = nullptr;
+    double *d_partial = nullptr;
+    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)n_window * nwarp);
+    size_t smem_full = sizeof(double) * 3 * (size_t)p->T + extra;
+    size_t budget = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;
+    bool use_smem = smem_full <= budget && !env_int("AMOFB_MSD_NO_SMEM", 0);
+    size_t smem = use_smem ? smem_full : extra;
+    if (extra > budget) return amofb_fail(ctx, AMOFB_ERR_ARG, "too many window lengths (%d) for one pass", n_window);
+    int per_sm = 1;
+    if (use_smem) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_msd_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msd_window<true>, threads, smem));
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_msd_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msd_window<false>, threads, smem));
+    }
+    if (per_sm < 1) return amofb_fail(ctx, AMOFB_ERR_CUDA, "window kernel does not fit on an SM");
+    int grid = std::max(1, std::min(p->n, ctx->num_sms * per_sm));
+    int rc = AMOFB_OK;
+    if ((rc = dev_alloc(ctx, &d_window, (size_t)n_window))) return rc;
+    if ((rc = dev_alloc(ctx, &d_partial, (size_t)grid * S * n_window))) { cudaFree(d_window); return rc; }
+    std::vector<double> part((size_t)grid * S * n_window);
+    cudaError_t e = cudaMemcpyAsync(d_window, window, sizeof(int) * n_window, cudaMemcpyHostToDevice, ctx->s_compute);
+    if (e == cudaSuccess) {
+        if (use_smem) k_msd_window<true><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);
+        else k_msd_window<false><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, ctx->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
+    cudaFree(d_window);
+    cudaFree(d_partial);
+    CUDA_TRY(ctx, e);
+    for (int i = 0; i < S * n_window; ++i) {
+        double s = 0.0;
+        for (int b = 0; b < grid; ++b) s += part[(size_t)b * S * n_window + i];   // fixed order: deterministic
+        sums[i] = s;
+    }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_msd_direct(amofb_ctx *ctx, double *sums) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_direct"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_direct needs the untouched positions");
+    if (!sums) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
+    for (int k = 0; k < p->T; ++k) {
+        const double *c = p->cell.data() + 9 * (size_t)k;
+        if (c[1] != 0.0 || c[2] != 0.0 || c[3] != 0.0 || c[5] != 0.0 || c[6] != 0.0 || c[7] != 0.0)
+            return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %d: DirectMsd only works for orthogonal cells", k);
+    }
+    k_msd_direct<<<(p->n + 127) / 128, 128, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->n, p->T);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    p->consumed = true;
+    std::vector<uint8_t> spec((size_t)p->n);
+    CUDA_TRY(ctx, cudaMemcpy(spec.data(), p->d_species, (size_t)p->n, cudaMemcpyDeviceToHost));
+    std::vector<double> w((size_t)p->n);
+    double *d_w = nullptr, *d_out = nullptr;
+    AMOFB_TRY(dev_alloc(ctx, &d_w, (size_t)p->n));
+    int rc = dev_alloc(ctx, &d_out, (size_t)p->T);
+    for (int s = 0; s < p->S && rc == AMOFB_OK; ++s) {
+        for (int i = 0; i < p->n; ++i) w[i] = spec[i] == s ? 1.0 : 0.0;
+        cudaError_t e = cudaMemcpy(d_w, w.data(), sizeof(double) * p->n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { rc = amofb_fail(ctx, AMOFB_ERR_CUDA, "msd_direct: %s", cudaGetErrorString(e)); break; }
+        rc = msd_frame_sums<1>(ctx, p, d_w, d_out);
+        if (rc) break;
+        e = cudaMemcpy(sums + (size_t)s * p->T, d_out, sizeof(double) * p->T, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { rc = amofb_fail(ctx, AMOFB_ERR_CUDA, "msd_direct: %s", cudaGetErrorString(e)); break; }
+    }
+    cudaFree(d_w);
+    cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int amofb_msd_get_positions(amofb_ctx *ctx, double *pos) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_get_positions"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "positions were already transformed in place");
+    if (!pos) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
+    const size_t fr = 3 * (size_t)p->n;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_copy));
+    for (int done = 0; done < p->T;) {
+        int nf = std::min(p->stage_frames, p->T - done);
+        dim3 grid((p->n + 31) / 32, (nf + 31) / 32);
+        k_msd_untranspose<<<grid, 256, 0, ctx->s_compute>>>(p->d_P, p->d_stage[0], p->n, p->T, done, nf);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(pos + fr * done, p->d_stage[0], sizeof(double) * fr * nf, cudaMemcpyDeviceToHost, ctx->s_compute));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+        done += nf;
+    }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_msd_end(amofb_ctx *ctx) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->msd) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_end before amofb_msd_begin");
+    msd_release(ctx);
+    return AMOFB_OK;
+}

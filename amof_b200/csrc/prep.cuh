@@ -1,0 +1,135 @@
+// prep.cuh -- GPU-built linked-cell list for a batch of frames (kernel K1 of SURVEY.md 2.1).
+//
+// Three launches per batch, all O(atoms):
+//   k_cell_assign   wrap every atom into its cell (P1, P2), find its linked cell, take a slot in it
+//   k_cell_scan     one block per frame: exclusive scan of the cell populations
+//   k_cell_scatter  write the wrapped atoms, ordered by cell, as 32-byte records {x, y, z, species}
+// The order of atoms inside a cell depends on atomic scheduling; every consumer only counts, so the
+// integers it produces do not.
+#pragma once
+#include "common.cuh"
+
+struct __align__(16) SAtom {
+    double x, y, z;
+    long long s;   // species | linked-cell coordinates (8 bytes wide so one atom is two 16-byte loads)
+};
+
+// one sorted atom = two read-only 16-byte loads
+__device__ __forceinline__ SAtom load_satom(const SAtom *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    SAtom s;
+    s.x = a.x; s.y = a.y; s.z = b.x; s.s = __double_as_longlong(b.y);
+    return s;
+}
+
+struct PrepArgs {
+    const double *raw;        // [F][N][3]
+    const FrameGeom *geom;    // [F]
+    const uint8_t *species;   // [N]
+    uint32_t *cell_count;     // [sum(ncell+1)]
+    uint32_t *cell_start;     // [sum(ncell+1)]
+    uint32_t *cid;            // [F*N]
+    uint32_t *rank;           // [F*N]
+    SAtom *sorted;            // [F*N]
+    int n_atoms;
+    int n_frames;
+};
+
+__device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__restrict__ p, double *pw, int *c) {
+    double px = p[0], py = p[1], pz = p[2];
+    double f[3], w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        f[k] = (px * g.inv[0 + k] + py * g.inv[3 + k]) + pz * g.inv[6 + k];   // P1
+        w[k] = floor(f[k]);
+    }
+    pw[0] = px - ((w[0] * g.cell[0] + w[1] * g.cell[3]) + w[2] * g.cell[6]);  // P2
+    pw[1] = py - ((w[0] * g.cell[1] + w[1] * g.cell[4]) + w[2] * g.cell[7]);
+    pw[2] = pz - ((w[0] * g.cell[2] + w[1] * g.cell[5]) + w[2] * g.cell[8]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double gk = f[k] - w[k];                      // in [0,1) for finite input
+        int ck = (gk >= 0.0) ? (int)(gk * (double)g.nc[k]) : 0;
+        if (ck > g.nc[k] - 1) ck = g.nc[k] - 1;
+        c[k] = ck;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
+    long long total = (long long)a.n_frames * a.n_atoms;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int f = (int)(idx / a.n_atoms);
+        const FrameGeom &g = a.geom[f];
+        double pw[3];
+        int c[3];
+        wrap_atom(g, a.raw + 3 * idx, pw, c);
+        uint32_t cid = (uint32_t)((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+        a.cid[idx] = cid;
+        a.rank[idx] = atomicAdd(&a.cell_count[g.cs_off + cid], 1u);
+    }
+}
+
+// one block per frame; writes ncell+1 entries (last = number of atoms)
+__global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    int f = blockIdx.x;
+    const FrameGeom &g = a.geom[f];
+    const uint32_t *cnt = a.cell_count + g.cs_off;
+    uint32_t *out = a.cell_start + g.cs_off;
+    int n = g.ncell;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        uint32_t v = (i < n) ? cnt[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sums[lane];
+            uint32_t wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - ws;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t excl = carry + warp_sums[warp] + incl - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
+    long long total = (long long)a.n_frames * a.n_atoms;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int f = (int)(idx / a.n_atoms);
+        int i = (int)(idx - (long long)f * a.n_atoms);
+        const FrameGeom &g = a.geom[f];
+        double pw[3];
+        int c[3];
+        wrap_atom(g, a.raw + 3 * idx, pw, c);
+        uint32_t dst = a.cell_start[g.cs_off + a.cid[idx]] + a.rank[idx];
+        SAtom s;
+        s.x = pw[0]; s.y = pw[1]; s.z = pw[2];
+        // species | c0 << 8 | c1 << 20 | c2 << 32   (nc <= 1024 per axis)
+        s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
+        a.sorted[(long long)f * a.n_atoms + dst] = s;
+    }
+}

@@ -1,0 +1,117 @@
+"""
+Trajectory ingest: ``list[ase.Atoms]`` (or anything indexable with ``len``) -> contiguous float64 chunks.
+
+aMOF's only trajectory contract is "an indexable, re-iterable sequence of ase.Atoms"
+(/root/reference/amof/rdf.py:71-88, amof/cn.py:77, amof/bad.py:149, amof/msd.py:218-237).  The GPU path wants
+``positions[F][N][3]`` + ``cell[F][3][3]`` blocks in page-locked memory, so frames are packed chunk by chunk into
+two alternating pinned buffers: while the GPU works on chunk k the interpreter packs chunk k+1.
+
+:class:`ArrayTrajectory` is an array-backed trajectory (still a valid aMOF trajectory: indexing yields Atoms)
+whose chunks are handed to the GPU without any per-frame Python work.
+"""
+import numpy as np
+
+from . import _dist
+from .atoms import Atoms
+
+
+class ArrayTrajectory:
+    """A trajectory stored as arrays: ``numbers[N]``, ``positions[T][N][3]``, ``cells[T][3][3]`` (or one [3][3])."""
+
+    def __init__(self, numbers, positions, cells, masses=None):
+        self.numbers = np.asarray(numbers, dtype=np.int64)
+        self.positions = np.asarray(positions, dtype=np.float64)
+        if self.positions.ndim != 3 or self.positions.shape[1:] != (len(self.numbers), 3):
+            raise ValueError("positions must be [T][N][3]")
+        cells = np.asarray(cells, dtype=np.float64)
+        if cells.shape == (3, 3):
+            cells = np.broadcast_to(cells, (self.positions.shape[0], 3, 3))
+        self.cells = np.ascontiguousarray(cells).reshape(self.positions.shape[0], 3, 3)
+        self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)
+
+    def __len__(self):
+        return self.positions.shape[0]
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return ArrayTrajectory(self.numbers, self.positions[k], self.cells[k], self.masses)
+        a = Atoms(numbers=self.numbers, positions=self.positions[k], cell=self.cells[k], masses=self.masses)
+        a._parent = (self, k)
+        return a
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+def _positions_of(atoms):
+    p = getattr(atoms, "positions", None)
+    return atoms.get_positions() if p is None else p
+
+
+def _cell_of(atoms):
+    return np.asarray(atoms.get_cell(), dtype=np.float64).reshape(3, 3)
+
+
+def species_index(numbers):
+    """atomic numbers -> (sorted unique Z, uint8 index per atom).  The index order is internal; output column
+    order is decided by the callers exactly as the reference does (``list(set(Z))``)."""
+    numbers = np.asarray(numbers)
+    zs = np.unique(numbers)
+    if len(zs) > 16:
+        raise ValueError("more than 16 chemical species are not supported by libamofb (AMOFB_MAX_SPECIES)")
+    return [int(z) for z in zs], np.searchsorted(zs, numbers).astype(np.uint8)
+
+
+def frame_range(n_frames, distributed=None):
+    """Contiguous block of frames this rank owns (frames shard naturally)."""
+    rank, world = _dist.rank_world(distributed)
+    lo = (n_frames * rank) // world
+    hi = (n_frames * (rank + 1)) // world
+    return lo, hi
+
+
+def check_same_atoms(trajectory, numbers, lo, hi):
+    """The C ABI takes one species vector per analysis; aMOF trajectories keep atom order fixed."""
+    if isinstance(trajectory, ArrayTrajectory):
+        return
+    for k in range(lo, hi):
+        z = trajectory[k].get_atomic_numbers()
+        if len(z) != len(numbers) or not np.array_equal(z, numbers):
+            raise ValueError("frame %d has different atoms (count or order) than frame 0; "
+                             "amof_b200 needs a fixed atom order over the trajectory" % k)
+
+
+def iter_chunks(trajectory, lo, hi, backend, target_bytes=64 << 20):
+    """Yield (positions[F][N][3], cell[F][3][3]) for frames [lo, hi).
+
+    ArrayTrajectory: zero-copy slices.  Otherwise frames are packed into two alternating page-locked buffers
+    obtained from the backend's context (plain numpy buffers when the backend has none)."""
+    if hi <= lo:
+        return
+    if isinstance(trajectory, ArrayTrajectory):
+        n = max(len(trajectory.numbers), 1)
+        step = max(1, int(target_bytes // (24 * n)))
+        for a in range(lo, hi, step):
+            b = min(hi, a + step)
+            yield trajectory.positions[a:b], trajectory.cells[a:b]
+        return
+    n = len(trajectory[lo])
+    step = max(1, min(hi - lo, int(target_bytes // (24 * max(n, 1)))))
+    ctx = getattr(backend, "ctx", None)
+    if ctx is not None:
+        bufs = [ctx.scratch("frames%d" % i, (step, n, 3)) for i in range(2)]
+    else:
+        bufs = [np.empty((step, n, 3)) for _ in range(2)]
+    which = 0
+    for a in range(lo, hi, step):
+        b = min(hi, a + step)
+        buf = bufs[which]
+        which ^= 1
+        if ctx is not None:
+            ctx.sync_copies()            # the copy that last read this buffer has finished
+        cells = np.empty((b - a, 3, 3))
+        for k in range(a, b):
+            fr = trajectory[k]
+            buf[k - a] = _positions_of(fr)
+            cells[k - a] = _cell_of(fr)
+        yield buf[:b - a], cells

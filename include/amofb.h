@@ -1,0 +1,161 @@
+/*
+ * amofb.h -- C ABI of libamofb.so, the B200 (sm_100a) implementation of aMOF's
+ * frame-parallel structural-analysis hot path.
+ *
+ * The reference (coudertlab/amof) is pure Python and has NO plugin / FFI interface of its own
+ * (SURVEY.md 8(b)); its hot arithmetic is delegated to asap3's C++ extension and to ase/numpy.
+ * This header is therefore the NEW boundary: each entry point names the reference interface it
+ * replaces.  The Python classes in amof_b200/ (same names and signatures as amof.rdf / amof.cn /
+ * amof.bad / amof.msd) are its only in-tree caller, through ctypes; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative AMOFB_ERR_* code;
+ *     amofb_last_error(ctx) gives the message.  No C++ exception crosses the ABI.
+ *   - positions are double[n_frames][n_atoms][3] (Angstrom), cells double[n_frames][3][3] with the
+ *     lattice vectors as rows -- exactly ase.Atoms.get_positions() / get_cell() stacked per frame.
+ *     All three directions are periodic (the reference assumes pbc=True throughout).
+ *   - species are small indices 0..n_species-1 (uint8), one per atom, constant over the trajectory.
+ *   - the caller owns every pointer it passes; the library owns device memory, pinned staging and
+ *     streams.  "push" calls enqueue work and may return before it has run; "finish"/"sync" wait.
+ *   - one ctx per GPU; a ctx is not thread-safe, distinct ctxs are independent.
+ *   - there is NO CPU fallback: without a CUDA device amofb_create fails.
+ *   - integer outputs (histograms, neighbour counts) are bit-exact with oracle/amof_oracle.c;
+ *     normalisation to g(r), densities and means stays in the caller (fp64 numpy).
+ */
+#ifndef AMOFB_H
+#define AMOFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMOFB_OK 0
+#define AMOFB_ERR_ARG (-1)      /* bad argument / call order            */
+#define AMOFB_ERR_CUDA (-2)     /* CUDA runtime error                   */
+#define AMOFB_ERR_STATE (-3)    /* begin/push/finish called out of turn */
+#define AMOFB_ERR_GEOMETRY (-4) /* singular cell, cutoff precondition, neighbour overflow */
+#define AMOFB_ERR_MEMORY (-5)
+
+#define AMOFB_MAX_SPECIES 16
+#define AMOFB_BAD_MAX_CN 32     /* a centre with more B-neighbours than this is a geometry error */
+
+typedef struct amofb_ctx amofb_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int amofb_create(int device, amofb_ctx **out);
+int amofb_destroy(amofb_ctx *ctx);
+const char *amofb_last_error(const amofb_ctx *ctx); /* valid until the next call on ctx */
+const char *amofb_version(void);
+/* Block until everything enqueued on ctx has finished (used by benchmarks to close a timed region). */
+int amofb_sync(amofb_ctx *ctx);
+/* Block until every host->device copy enqueued so far has finished (kernels may still be running): after this the
+ * caller may overwrite the pinned buffers it passed to earlier push/load calls. */
+int amofb_sync_copies(amofb_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py reports it as gpu_launches). */
+int64_t amofb_launch_count(const amofb_ctx *ctx);
+/* Sum of CUDA-event durations (ms) and launch count of the pair kernel since the last call with
+ * reset != 0; timing is only collected after amofb_set_profiling(ctx, 1). */
+int amofb_set_profiling(amofb_ctx *ctx, int enabled);
+int amofb_pair_kernel_time(amofb_ctx *ctx, double *total_ms, int64_t *launches, int reset);
+
+/* Page-locked host buffers for callers that want zero-copy streaming (bench.py, the Python classes). */
+int amofb_host_alloc(amofb_ctx *ctx, uint64_t bytes, void **out);
+int amofb_host_free(amofb_ctx *ctx, void *ptr);
+/* Device buffers for device-resident trajectories (amofb_*_push_device). */
+int amofb_device_alloc(amofb_ctx *ctx, uint64_t bytes, void **out);
+int amofb_device_free(amofb_ctx *ctx, void *ptr);
+int amofb_memcpy_h2d(amofb_ctx *ctx, void *dst_device, const void *src_host, uint64_t bytes);
+int amofb_memcpy_d2h(amofb_ctx *ctx, void *dst_host, const void *src_device, uint64_t bytes);
+
+/* ---- pair analysis: partial RDF histograms and cutoff neighbour counts ---------------------
+ * Replaces, per frame,
+ *   asap3.analysis.rdf.RadialDistributionFunction(atoms, rMax, nBins) / .atoms = frame / .update()
+ *       (call sites /root/reference/amof/rdf.py:87-93 and :181)
+ *   ase.neighborlist.neighbor_list('ij', atoms, cutoff_dict) + the counting loops
+ *       (/root/reference/amof/atom.py:72-87, amof/cn.py:58-74)
+ * in ONE pass over the trajectory.
+ *
+ * begin : nbins > 0 enables the RDF histogram with bin width rmax/nbins (bin = (int)(d / (rmax/nbins)),
+ *         counted iff < nbins); cn_cutoff != NULL (double[n_species][n_species], symmetric, 0 = pair not
+ *         listed) enables per-frame neighbour counts with the strict test d < cutoff[Zi][Zj].
+ * push  : n_frames frames in host memory (pinned memory is copied asynchronously, pageable memory is
+ *         staged).  push_device: positions already in device memory (cells still on the host).
+ * finish: hist       uint64[n_species][n_species][nbins]  directed pair counts, summed over frames (or NULL)
+ *         cn_counts  uint64[cn_frames][n_species][n_species] directed neighbour pairs per frame (or NULL);
+ *                    cn_frames must equal the number of frames pushed
+ *         n_frames_out, volume_sum_out: frames seen and the sum of their cell volumes
+ *         finish ends the accumulation; begin may be called again on the same ctx.
+ */
+int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species,
+                     double rmax, int nbins, const double *cn_cutoff);
+int amofb_pair_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell);
+int amofb_pair_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell);
+int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
+                      int64_t *n_frames_out, double *volume_sum_out);
+
+/* The accumulator trio SURVEY.md 8(b) proposed, as thin aliases of the pair analysis:
+ * amofb_rdf_* = histogram only, amofb_cn_* = neighbour counts only. */
+int amofb_rdf_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, double rmax, int nbins);
+int amofb_rdf_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell);
+int amofb_rdf_finish(amofb_ctx *ctx, uint64_t *hist, int64_t *n_frames_out, double *volume_sum_out);
+int amofb_cn_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, const double *cn_cutoff);
+int amofb_cn_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell);
+int amofb_cn_finish(amofb_ctx *ctx, uint64_t *cn_counts, int64_t cn_frames);
+
+/* ---- bond-angle distributions ---------------------------------------------------------------
+ * Replaces amof.atom.get_neighborlist + Bad.bad_BAB / BadByCn.bad_BAB + np.histogram
+ * (/root/reference/amof/bad.py:70-114,160 and :192-239,293): for every centre a of species A, all unordered
+ * pairs of its B-neighbours (neighbour list under cutoff[n_species][n_species]) give one angle in degrees,
+ * histogrammed on the edges k*dtheta, k = 0..nbins, split by the centre's number of B-neighbours.
+ *
+ * triples: int[n_triples][2] = (A, B) species indices, -1 = "X" (any species).
+ * finish : hist uint64[n_triples][AMOFB_BAD_MAX_CN+1][nbins]; dropped uint64[n_triples] counts angles that
+ *          np.histogram would drop (NaN from |cos| > 1 by rounding).
+ * Precondition (AMOFB_ERR_GEOMETRY otherwise): max cutoff < half the smallest perpendicular cell height.
+ */
+int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species,
+                    const double *cutoff, int n_triples, const int *triples, double dtheta, int nbins);
+int amofb_bad_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell);
+int amofb_bad_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell);
+int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *dropped, int64_t *n_frames_out);
+
+/* ---- mean-squared displacement --------------------------------------------------------------
+ * Replaces WindowMsd.compute_msd / compute_msd_of_m and trajectory.get_delta_pos
+ * (/root/reference/amof/msd.py:186-268, amof/trajectory.py:285-303).
+ *
+ * The trajectory is resident on the device for the whole computation (unwrapping is a scan over frames and
+ * window pairs span up to half the trajectory), so MSD is ATOM-sharded across GPUs: every rank holds all
+ * frames of its own atoms, and the only exchanges are the per-frame centre-of-mass sums and the final sums.
+ *
+ * begin      : n_frames x n_atoms (local atoms), masses[n_atoms], species[n_atoms], cell[n_frames][9].
+ * load       : copy frames [first, first+count) of the local atoms, host double[count][n_atoms][3].
+ * load_device: same from device memory.
+ * unwrap     : optional (WindowMsd(unwrap=True), msd.py:222-230): positions <- cumulative wrapped displacements.
+ * com_sums   : double[n_frames][4] = (sum m*x, sum m*y, sum m*z, sum m) over the LOCAL atoms.
+ * set_com    : double[n_frames][3] global centre of mass per frame (after the caller's allreduce).
+ * window     : sums[n_species][n_window] = sum over local atoms of species s and over k = m+1..T-1 of
+ *              |R_k - R_{k-m}|^2, R = COM-removed positions rebuilt from wrapped displacements.
+ *              The caller divides by N_species*(T-m) (quirk Q4 of SURVEY.md) after its allreduce.
+ * direct     : DirectMsd.compute_species_msd (msd.py:81-105), orthogonal cells only:
+ *              sums[n_species][n_frames] = sum over local atoms of |r_t - r_0|^2.
+ * get_positions: copy the (unwrapped and/or COM-shifted) positions back, host double[n_frames][n_atoms][3].
+ */
+int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const double *masses, const uint8_t *species,
+                    int n_species, const double *cell);
+int amofb_msd_load(amofb_ctx *ctx, int first_frame, int count, const double *pos);
+int amofb_msd_load_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device);
+int amofb_msd_unwrap(amofb_ctx *ctx);
+int amofb_msd_com_sums(amofb_ctx *ctx, double *sums);
+int amofb_msd_set_com(amofb_ctx *ctx, const double *com);
+int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window, double *sums);
+int amofb_msd_direct(amofb_ctx *ctx, double *sums);
+int amofb_msd_get_positions(amofb_ctx *ctx, double *pos);
+int amofb_msd_end(amofb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMOFB_H */

@@ -1,0 +1,90 @@
+"""
+Regenerates the committed fixtures from the read-only reference checkout.  Run in the build
+container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Writes
+  amof_b200/data/zif4_unit_cell.json    the 272-atom ZIF-4 frame of /root/reference/examples/files/ZIF-4.xyz
+                                        (cell, symbols, positions) -- input of the C1 config and the
+                                        building block of the synthetic C2-C5 supercells
+  tests/golden/zif4_known_answers.json  the known answers of BASELINE.md section 4, recomputed with the
+                                        numpy twin of the oracle (brute force over all images)
+
+The reference cannot be imported here (ase / asap3 absent), so these are restatement-derived values:
+parity stays "unpinned" (oracle/amof_oracle.c header).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from amof_b200.atoms import read_extxyz  # noqa: E402
+from oracle import np_oracle as npo  # noqa: E402
+
+SRC = "/root/reference/examples/files/ZIF-4.xyz"
+
+
+def main():
+    a = read_extxyz(SRC, 0)
+    unit = {
+        "source": "coudertlab/amof examples/files/ZIF-4.xyz (frame 0)",
+        "cell": [[repr(float(x)) for x in row] for row in a.cell],
+        "symbols": a.get_chemical_symbols(),
+        "positions": [[repr(float(x)) for x in row] for row in a.positions],
+    }
+    os.makedirs(os.path.join(ROOT, "amof_b200", "data"), exist_ok=True)
+    with open(os.path.join(ROOT, "amof_b200", "data", "zif4_unit_cell.json"), "w") as fh:
+        json.dump(unit, fh, indent=0)
+
+    nums = a.get_atomic_numbers()
+    order = sorted(set(int(z) for z in nums))          # fixed order for the fixture: H, C, N, Zn
+    spec = np.array([order.index(int(z)) for z in nums], dtype=np.uint8)
+    S = len(order)
+    lengths = a.get_cell_lengths_and_angles()[0:3]
+    rmax = float(np.min(lengths) / 2)
+    bins = int(rmax // 0.01)
+    hist = npo.rdf_hist(a.positions, a.cell, spec, S, rmax, bins)
+
+    def cn(pair, cutoff):
+        za, zb = pair
+        cut = np.zeros((S, S))
+        cut[order.index(za), order.index(zb)] = cut[order.index(zb), order.index(za)] = cutoff
+        return int(npo.cn_counts(a.positions, a.cell, spec, S, cut)[order.index(za), order.index(zb)])
+
+    cut = np.zeros((S, S))
+    cut[order.index(30), order.index(7)] = cut[order.index(7), order.index(30)] = 2.5
+    ang = npo.bad_angles(a.positions, a.cell, spec, cut, order.index(30), order.index(7))
+    flat = sorted(sum(ang.values(), []))
+    known = {
+        "species_order": order,
+        "n_atoms": len(a),
+        "composition": {str(z): int((nums == z).sum()) for z in order},
+        "volume": a.get_volume(),
+        "rdf_default": {
+            "rmax": rmax, "bins": bins,
+            "directed_pairs_total": int(hist.sum()),
+            "directed_pairs": {"%d-%d" % (order[i], order[j]): int(hist[i, j].sum()) for i in range(S) for j in range(S)},
+            "hist_Zn_N": [int(x) for x in hist[order.index(30), order.index(7)]],
+            "hist_total": [int(x) for x in hist.sum(axis=(0, 1))],
+        },
+        "cn_directed_pairs": {
+            "Zn-N@2.5": cn((30, 7), 2.5), "N-Zn@2.5": cn((7, 30), 2.5), "Zn-Zn@7.0": cn((30, 30), 7.0),
+            "C-N@1.728": cn((6, 7), 1.728), "C-C@1.752": cn((6, 6), 1.752),
+        },
+        "bad_N_Zn_N@2.5": {"by_cn": {str(k): len(v) for k, v in ang.items()}, "count": len(flat),
+                           "min": flat[0], "max": flat[-1], "mean": float(np.mean(flat)),
+                           "angles_sorted": flat},
+    }
+    with open(os.path.join(ROOT, "tests", "golden", "zif4_known_answers.json"), "w") as fh:
+        json.dump(known, fh, indent=1)
+    print("wrote fixtures:", known["rdf_default"]["directed_pairs_total"], known["cn_directed_pairs"],
+          known["bad_N_Zn_N@2.5"]["count"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""GPU parity of the bond-angle analysis against the CPU oracle, through the C ABI (bit-exact histograms)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import random_box
+from oracle import c_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "zif4_known_answers.json")
+MAXCN = 32
+
+
+def _oracle(pos, cell, spec, S, cut, triples, dtheta, nbins):
+    hist = np.zeros((len(triples), MAXCN + 1, nbins), dtype=np.uint64)
+    dropped = np.zeros(len(triples), dtype=np.uint64)
+    for f in range(len(pos)):
+        for t, (A, B) in enumerate(triples):
+            _, d = orc.bad_hist(pos[f], cell[f], spec, S, cut, A, B, dtheta, nbins, max_cn=MAXCN, hist=hist[t])
+            dropped[t] += d
+    return hist, dropped
+
+
+def test_zif4_golden(backend, zif4):
+    gold = json.load(open(GOLD))
+    order = gold["species_order"]
+    spec = np.array([order.index(int(z)) for z in zif4.numbers], dtype=np.uint8)
+    cut = np.zeros((4, 4))
+    cut[3, 2] = cut[2, 3] = 2.5
+    nbins = int(180 // 0.05) + 1
+    assert nbins == 3600
+    hist, dropped, nf = backend.bad_counts(spec, 4, [(zif4.positions[None], zif4.cell[None])], cut, [(3, 2), (2, 3)], 0.05, nbins)
+    g = gold["bad_N_Zn_N@2.5"]
+    assert int(hist[0].sum()) == g["count"] == 96 and int(hist[0, 4].sum()) == 96      # every Zn has 4 N
+    assert int(hist[1].sum()) == 0 and int(dropped.sum()) == 0 and nf == 1
+    edges = np.arange(nbins + 1) * 0.05
+    want = np.histogram(g["angles_sorted"], bins=edges)[0]
+    assert np.array_equal(hist[0].sum(axis=0), want.astype(np.uint64))
+
+
+@pytest.mark.parametrize("seed,n,tri,size,dtheta", [
+    (1, 400, False, 14.0, 0.05),
+    (2, 700, True, 16.0, 0.05),
+    (3, 900, True, 18.0, 1.0),
+    (4, 300, True, 12.0, 0.7),      # 180 // 0.7 = 257 -> last edge 180.6 > 180
+    (5, 500, False, 15.0, 7.0),     # 180 // 7 = 25 -> last edge 182
+])
+def test_random_boxes(backend, seed, n, tri, size, dtheta):
+    S = 3
+    T = 2
+    frames = [random_box(seed * 10 + f, n, S, tri, size, scale_pos=2.0) for f in range(T)]
+    spec = frames[0][2]
+    pos = np.array([f[0] for f in frames])
+    cell = np.array([f[1] for f in frames])
+    cut = np.array([[2.6, 3.0, 0.0], [3.0, 0.0, 2.8], [0.0, 2.8, 2.4]])
+    triples = [(0, 1), (1, 0), (1, 2), (2, 2), (0, -1), (-1, -1)]
+    nbins = int(180 // dtheta) + 1
+    hist, dropped, nf = backend.bad_counts(spec, S, [(pos, cell)], cut, triples, dtheta, nbins)
+    want, wdrop = _oracle(pos, cell, spec, S, cut, triples, dtheta, nbins)
+    assert int(want.sum()) > 50
+    assert np.array_equal(hist, want)
+    assert np.array_equal(dropped, wdrop)
+    assert nf == T
+
+
+def test_collinear_and_degenerate_angles(backend):
+    """0 and 180 degree angles sit exactly on histogram edges; a short dtheta grid must agree with the oracle."""
+    cell = np.diag([20.0, 20.0, 20.0])
+    pos = np.array([[10.0, 10.0, 10.0], [11.5, 10.0, 10.0], [8.5, 10.0, 10.0], [10.0, 11.5, 10.0],
+                    [10.0, 10.0, 8.2], [12.0, 10.0, 10.0]])
+    spec = np.array([0, 1, 1, 1, 1, 1], dtype=np.uint8)
+    cut = np.array([[0.0, 2.5], [2.5, 0.0]])
+    for dtheta in (0.05, 1.0, 90.0, 45.0):
+        nbins = int(180 // dtheta) + 1
+        hist, dropped, _ = backend.bad_counts(spec, 2, [(pos[None], cell[None])], cut, [(0, 1)], dtheta, nbins)
+        want, wdrop = _oracle(pos[None], cell[None], spec, 2, cut, [(0, 1)], dtheta, nbins)
+        assert np.array_equal(hist, want) and np.array_equal(dropped, wdrop)
+        assert int(hist.sum() + dropped.sum()) == 10          # C(5, 2) angles around the centre
+
+
+def test_cutoff_precondition(backend):
+    pos, cell, spec = random_box(7, 50, 2, False, 6.0)
+    cut = np.full((2, 2), 3.5)      # above half the cell height
+    with pytest.raises(ValueError):
+        backend.bad_counts(spec, 2, [(pos[None], cell[None])], cut, [(0, 1)], 0.05, 3600)

@@ -1,0 +1,111 @@
+"""GPU parity of the MSD analysis against the CPU oracle, through the C ABI (1e-12 relative, north_star)."""
+import numpy as np
+import pytest
+
+from conftest import random_box
+from oracle import c_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _walk(seed, T, n, tri=True, size=12.0, step=0.4, wrapped=True, nspec=3):
+    rng = np.random.default_rng(seed)
+    pos0, cell0, spec = random_box(seed, n, nspec, tri, size)
+    pos = pos0[None] + np.cumsum(rng.normal(scale=step, size=(T, n, 3)), axis=0)
+    cells = np.array([cell0 * (1.0 + 0.001 * np.sin(k)) for k in range(T)])
+    if wrapped:
+        for k in range(T):
+            f = pos[k] @ np.linalg.inv(cells[k])
+            pos[k] = (f - np.floor(f)) @ cells[k]
+    masses = np.array([1.008, 12.011, 65.38, 14.007])[spec]
+    return pos, cells, spec, masses
+
+
+def _gpu_window(backend, pos, cells, spec, masses, S, window, unwrap):
+    T = len(pos)
+    with backend.msd_open(T, masses, spec, S, cells) as s:
+        s.load(0, pos[:T // 2])
+        s.load(T // 2, pos[T // 2:])
+        new_pos = None
+        if unwrap:
+            s.unwrap()
+            new_pos = s.get_positions()
+        sums = s.com_sums()
+        com = sums[:, :3] / sums[:, 3:4]
+        s.set_com(com)
+        raw = s.window(np.asarray(window, dtype=np.int32))
+    n_of = np.bincount(spec, minlength=S).astype(np.float64)
+    msd = raw / n_of[:, None] / (T - np.asarray(window, dtype=np.float64))[None, :]
+    return msd, com, new_pos
+
+
+@pytest.mark.parametrize("seed,T,n,tri,unwrap", [
+    (1, 40, 50, False, False),
+    (2, 65, 33, True, False),
+    (3, 50, 70, True, True),
+    (4, 97, 1, True, False),
+    (5, 33, 300, False, True),
+])
+def test_window_msd(backend, seed, T, n, tri, unwrap):
+    S = 3
+    pos, cells, spec, masses = _walk(seed, T, n, tri)
+    window = np.arange(0, T // 2, 3)
+    got, com, new_pos = _gpu_window(backend, pos, cells, spec, masses, S, window, unwrap)
+    want, mutated = orc.msd_window(pos, cells, masses, spec, S, window, unwrap=unwrap)
+    present = np.bincount(spec, minlength=S) > 0
+    assert np.all(got[present][:, 0] == 0.0)
+    np.testing.assert_allclose(got[present], want[present], rtol=RTOL, atol=1e-13)
+    if unwrap:
+        # oracle returns unwrapped AND com-shifted positions; undo the shift with the GPU's own com
+        np.testing.assert_allclose(new_pos - com[:, None, :], mutated, rtol=0, atol=1e-9)
+
+
+def test_msd_get_positions_roundtrip(backend):
+    pos, cells, spec, masses = _walk(9, 37, 45, True)
+    with backend.msd_open(len(pos), masses, spec, 3, cells) as s:
+        s.load(0, pos)
+        back = s.get_positions()
+        sums = s.com_sums()
+    assert np.array_equal(back, pos)
+    want = (masses[None, :, None] * pos).sum(axis=1)
+    np.testing.assert_allclose(sums[:, :3], want, rtol=1e-13)
+    np.testing.assert_allclose(sums[:, 3], masses.sum(), rtol=1e-15)
+
+
+def test_long_series_global_path(backend, monkeypatch):
+    """T too long for shared memory staging -> the global-memory variant of the window kernel."""
+    monkeypatch.setenv("AMOFB_MSD_NO_SMEM", "1")
+    pos, cells, spec, masses = _walk(12, 60, 40, True)
+    window = np.arange(0, 30, 5)
+    got, _, _ = _gpu_window(backend, pos, cells, spec, masses, 3, window, False)
+    want, _ = orc.msd_window(pos, cells, masses, spec, 3, window)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-13)
+
+
+def test_direct_msd(backend):
+    pos, cells, spec, masses = _walk(21, 45, 60, tri=False, step=0.3)
+    with backend.msd_open(len(pos), masses, spec, 3, cells) as s:
+        s.load(0, pos)
+        raw = s.direct()
+    n_of = np.bincount(spec, minlength=3)
+    for sp in range(3):
+        want = orc.msd_direct(pos, cells, spec, sp)
+        np.testing.assert_allclose(raw[sp] / n_of[sp], want, rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(raw.sum(axis=0) / len(spec), orc.msd_direct(pos, cells, spec, -1), rtol=RTOL, atol=1e-13)
+    tri = cells.copy()
+    tri[:, 1, 0] = 0.5
+    with backend.msd_open(len(pos), masses, spec, 3, tri) as s:
+        s.load(0, pos)
+        with pytest.raises(ValueError):
+            s.direct()
+
+
+def test_state_machine_errors(backend):
+    pos, cells, spec, masses = _walk(30, 20, 10, False)
+    with backend.msd_open(len(pos), masses, spec, 3, cells) as s:
+        s.load(0, pos)
+        with pytest.raises(RuntimeError):
+            s.window(np.array([0, 1], dtype=np.int32))          # no centre of mass yet
+        with pytest.raises(ValueError):
+            s.load(15, pos[:10])                                  # outside [0, T)
