@@ -43,6 +43,8 @@ SIGNATURES = {
     "amofb_launch_count": (C.c_int64, [_vp]),
     "amofb_set_profiling": (C.c_int, [_vp, C.c_int]),
     "amofb_pair_kernel_time": (C.c_int, [_vp, _dp, _i64p, C.c_int]),
+    "amofb_timer_mark": (C.c_int, [_vp, C.c_int]),
+    "amofb_timer_elapsed": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "amofb_host_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "amofb_host_free": (C.c_int, [_vp, _vp]),
     "amofb_device_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
@@ -194,6 +196,14 @@ class Context:
 
     def set_profiling(self, on):
         self.check(self.lib.amofb_set_profiling(self.h, 1 if on else 0))
+
+    def timer_mark(self, slot):
+        self.check(self.lib.amofb_timer_mark(self.h, int(slot)))
+
+    def timer_elapsed(self, a, b):
+        ms = C.c_double(0.0)
+        self.check(self.lib.amofb_timer_elapsed(self.h, int(a), int(b), C.byref(ms)))
+        return ms.value
 
     def pair_kernel_time(self, reset=True):
         ms, n = C.c_double(0.0), C.c_int64(0)

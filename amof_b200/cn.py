@@ -46,19 +46,21 @@ class CoordinationNumber(object):
         logger.info("Start computing coordination number for %s frames", len(trajectory))
         cutoff_dict = amatom.format_cutoff(nb_set_and_cutoff)
         zs, spec, res = _rdf.pair_histograms(trajectory, 0.0, 0, cn_cutoff=cutoff_dict, distributed=distributed)
-        counts = res["cn"]                                  # uint64 [T][S][S] directed neighbour pairs
+        self._assemble(nb_set_and_cutoff, step, zs, spec, res["cn"], len(trajectory))
+
+    def _assemble(self, nb_set_and_cutoff, step, zs, spec, counts, n_frames):
+        """counts uint64 [T][S][S] of directed neighbour pairs -> the reference's DataFrame (cn.py:67-82)."""
         n_of = np.bincount(spec, minlength=len(zs))
         idx = {z: k for k, z in enumerate(zs)}
         columns = {"Step": step}
         for nb_set in nb_set_and_cutoff.keys():
             a, b = tuple(atomic_numbers[i] for i in nb_set.split('-'))
             if a in idx and b in idx:
-                with np.errstate(invalid='ignore', divide='ignore'):
-                    columns[nb_set] = counts[:, idx[a], idx[b]].astype(np.float64) / float(n_of[idx[a]])
+                columns[nb_set] = counts[:, idx[a], idx[b]].astype(np.float64) / float(n_of[idx[a]])
             elif a in idx:
-                columns[nb_set] = np.zeros(len(trajectory))            # A atoms exist, none of their neighbours is B
+                columns[nb_set] = np.zeros(n_frames)            # A atoms exist, none of their neighbours is B
             else:
-                columns[nb_set] = np.full(len(trajectory), np.nan)     # np.mean([]) in the reference
+                columns[nb_set] = np.full(n_frames, np.nan)     # np.mean([]) in the reference
         self.data = pd.DataFrame(columns)
         self.counts = counts
         self.species = zs

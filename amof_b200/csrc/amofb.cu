@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "pair.cuh"
+#include "pair_tiled.cuh"
 #include "bad.cuh"
 #include "msd.cuh"
 
@@ -55,6 +56,7 @@ extern "C" int amofb_destroy(amofb_ctx *ctx) {
     bad_release(ctx);
     msd_release(ctx);
     for (auto &p : ctx->pending_pair_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &t : ctx->timer) if (t) cudaEventDestroy(t);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     delete ctx;
@@ -105,6 +107,25 @@ extern "C" int amofb_pair_kernel_time(amofb_ctx *ctx, double *total_ms, int64_t 
     if (total_ms) *total_ms = ctx->pair_ms;
     if (launches) *launches = ctx->pair_launches;
     if (reset) { ctx->pair_ms = 0.0; ctx->pair_launches = 0; }
+    return AMOFB_OK;
+}
+
+extern "C" int amofb_timer_mark(amofb_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) return AMOFB_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->timer[slot]) CUDA_TRY(ctx, cudaEventCreate(&ctx->timer[slot]));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->timer[slot], ctx->s_compute));
+    return AMOFB_OK;
+}
+extern "C" int amofb_timer_elapsed(amofb_ctx *ctx, int from_slot, int to_slot, double *ms) {
+    if (!ctx || !ms || from_slot < 0 || from_slot >= 8 || to_slot < 0 || to_slot >= 8) return AMOFB_ERR_ARG;
+    if (!ctx->timer[from_slot] || !ctx->timer[to_slot]) return amofb_fail(ctx, AMOFB_ERR_STATE, "timer slot never marked");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->timer[from_slot]));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->timer[to_slot]));
+    float f = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->timer[from_slot], ctx->timer[to_slot]));
+    *ms = f;
     return AMOFB_OK;
 }
 
@@ -352,6 +373,13 @@ struct PairState {
     size_t smem = 0;
     double r2search = 0.0, r2max = 0.0;
     float inv_dr_f = 0.f;
+    // tiled path (pair_tiled.cuh)
+    bool tiled = false;
+    PairTile *d_tiles = nullptr;
+    int *d_ntiles = nullptr, *d_flags = nullptr;
+    uint8_t *d_hard = nullptr;
+    int tile_cap = 0, tile_grid = 0, max_tiles = 0;
+    size_t tile_smem = 0, hard_bytes = 0;
 };
 
 static void pair_release(amofb_ctx *ctx) {
@@ -361,6 +389,7 @@ static void pair_release(amofb_ctx *ctx) {
     cudaStreamSynchronize(ctx->s_compute);
     batcher_release(p->bt);
     cudaFree(p->d_edge2); cudaFree(p->d_cnthr2); cudaFree(p->d_keyidx); cudaFree(p->d_slabs); cudaFree(p->d_hist);
+    cudaFree(p->d_tiles); cudaFree(p->d_ntiles); cudaFree(p->d_flags); cudaFree(p->d_hard);
     delete p;
     ctx->pair = nullptr;
 }
@@ -466,9 +495,43 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if (rc) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_hist, hist_n))) return fail(rc);
     cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * std::max<size_t>(hist_n, 1));
+    // tiled kernel: shared memory = fixed tables + as many staged atoms as still let two blocks share an SM
+    if (p->smem_hist && n_atoms > 0 && !env_int("AMOFB_PAIR_GENERIC", 0)) {
+        size_t fixed = smem_full + sizeof(int) * (TILE_MAX_ENTRIES + 1) + 64;
+        int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", 2);
+        size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
+        size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 512;
+        if (per_block > budget) per_block = budget;
+        long long cap = per_block > fixed ? (long long)((per_block - fixed) / sizeof(SAtom)) : 0;
+        int cap_env = env_int("AMOFB_TILE_CAP", 0);
+        if (cap_env > 0 && cap_env < cap) cap = cap_env;
+        if (cap >= 256) {
+            p->tile_cap = (int)cap;
+            p->tile_smem = fixed + sizeof(SAtom) * (size_t)cap;
+            int per_sm = 0;
+            cudaError_t e1 = p->has_cn
+                ? cudaFuncSetAttribute(k_pair_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem)
+                : cudaFuncSetAttribute(k_pair_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+            if (e1 == cudaSuccess)
+                e1 = p->has_cn ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_tiled<true>, TILE_THREADS, p->tile_smem)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_tiled<false>, TILE_THREADS, p->tile_smem);
+            if (e1 == cudaSuccess && per_sm >= 1) {
+                p->tiled = true;
+                p->tile_grid = ctx->num_sms * per_sm;
+                p->max_tiles = (int)std::min<size_t>(p->bt.cells_per_frame * p->bt.cap_frames, (size_t)1 << 26);
+                p->hard_bytes = p->bt.cells_per_frame * p->bt.cap_frames;
+                if ((rc = dev_alloc(ctx, &p->d_tiles, (size_t)p->max_tiles))) return fail(rc);
+                if ((rc = dev_alloc(ctx, &p->d_ntiles, 4))) return fail(rc);
+                if ((rc = dev_alloc(ctx, &p->d_flags, 1))) return fail(rc);
+                if ((rc = dev_alloc(ctx, &p->d_hard, p->hard_bytes))) return fail(rc);
+                cudaMemset(p->d_flags, 0, sizeof(int));
+            } else cudaGetLastError();
+        }
+    }
     if (p->smem_hist) {
-        if ((rc = dev_alloc(ctx, &p->d_slabs, hist_n * p->grid))) return fail(rc);
-        cudaMemset(p->d_slabs, 0, sizeof(unsigned long long) * hist_n * p->grid);
+        size_t nslab = (size_t)std::max(p->grid, p->tile_grid);
+        if ((rc = dev_alloc(ctx, &p->d_slabs, hist_n * nslab))) return fail(rc);
+        cudaMemset(p->d_slabs, 0, sizeof(unsigned long long) * hist_n * nslab);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { amofb_fail(ctx, AMOFB_ERR_CUDA, "pair_begin: %s", cudaGetErrorString(e)); return fail(AMOFB_ERR_CUDA); }
@@ -495,6 +558,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
         a.r2search = p->r2search; a.r2max = p->r2max; a.inv_dr_f = p->inv_dr_f;
         a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys; a.nbins = p->nbins;
         a.tiles_per_frame = (b.n_atoms + PAIR_TILE - 1) / PAIR_TILE;
+        a.hard_mask = nullptr; a.n_hard = nullptr;
         long long tiles = (long long)nf * a.tiles_per_frame;
         if (tiles > 0) {
             // smem-histogram mode always launches the full grid: every block owns a slab
@@ -504,6 +568,34 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 CUDA_TRY(ctx, cudaEventCreate(&e0));
                 CUDA_TRY(ctx, cudaEventCreate(&e1));
                 CUDA_TRY(ctx, cudaEventRecord(e0, ctx->s_compute));
+            }
+            // the tiled kernel needs every frame's half stencil to fit its offset table
+            bool tiled = p->tiled;
+            size_t ncell_total = 0;
+            long long columns = 0;
+            for (int f = 0; f < nf && tiled; ++f) {
+                const FrameGeom &g = s->h_geom[f];
+                int R = (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1);
+                if (R > TILE_MAX_ENTRIES || TILE_MAX_ENTRIES / R < 2 * g.m[2] + 1) tiled = false;
+                ncell_total += (size_t)g.ncell + 1;
+                columns += (long long)g.nc[0] * g.nc[1];
+            }
+            if (tiled) {
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles, 0, sizeof(int) * 4, ctx->s_compute));
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_hard, 0, ncell_total, ctx->s_compute));
+                PlanArgs pl;
+                pl.geom = s->d_geom; pl.cell_start = s->d_cell_start; pl.tiles = p->d_tiles; pl.n_tiles = p->d_ntiles;
+                pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles;
+                k_pair_plan<<<(unsigned)((columns + 127) / 128), 128, 0, ctx->s_compute>>>(pl);
+                TiledArgs ta;
+                ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;
+                ta.p.hard_mask = nullptr; ta.p.n_hard = nullptr;
+                if (p->has_cn) k_pair_tiled<true><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
+                else k_pair_tiled<false><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
+                ctx->launches += 2;
+                CUDA_TRY(ctx, cudaGetLastError());
+                a.hard_mask = p->d_hard;          // clean-up launch: only the home cells the plan could not tile
+                a.n_hard = p->d_ntiles + 1;
             }
             if (p->has_rdf && p->has_cn) { if (p->smem_hist) pair_launch<true, true, true>(ctx, p, a, grid); else pair_launch<true, true, false>(ctx, p, a, grid); }
             else if (p->has_rdf) { if (p->smem_hist) pair_launch<true, false, true>(ctx, p, a, grid); else pair_launch<true, false, false>(ctx, p, a, grid); }
@@ -553,8 +645,14 @@ extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_co
         if (hist) {
             if (!p->has_rdf) return amofb_fail(ctx, AMOFB_ERR_ARG, "hist requested but nbins was 0 at begin");
             const size_t hist_n = (size_t)p->nkeys * p->nbins;
+            if (p->d_flags) {
+                int flags = 0;
+                CUDA_TRY(ctx, cudaMemcpyAsync(&flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+                if (flags) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "tile list overflow (extremely inhomogeneous frame); rerun with AMOFB_PAIR_GENERIC=1");
+            }
             if (p->smem_hist) {
-                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, p->grid, (int)hist_n, p->d_hist);
+                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, std::max(p->grid, p->tile_grid), (int)hist_n, p->d_hist);
                 ctx->launches += 1;
                 CUDA_TRY(ctx, cudaGetLastError());
             }

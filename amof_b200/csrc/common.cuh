@@ -36,6 +36,7 @@ struct amofb_ctx {
     double pair_ms = 0.0;
     int64_t pair_launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_pair_events;
+    cudaEvent_t timer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     PairState *pair = nullptr;
     BadState *bad = nullptr;
     MsdState *msd = nullptr;

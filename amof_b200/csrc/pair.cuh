@@ -28,6 +28,8 @@ struct PairArgs {
     unsigned long long *slabs;    // [gridDim.x][nkeys*nbins]   (smem-histogram mode)
     unsigned long long *ghist;    // [nkeys*nbins]              (global-atomic mode)
     unsigned long long *cn_out;   // [F][nkeys]
+    const uint8_t *hard_mask;     // optional: batch-wide per-cell mask, only atoms of marked home cells are processed
+    const int *n_hard;            // optional: number of marked cells (0 -> the launch returns at once)
     double r2search;              // a pair matters iff d2 < r2search
     double r2max;                 // = edge2[nbins]
     float inv_dr_f;
@@ -46,6 +48,7 @@ __device__ __forceinline__ int rdf_bin(double d2, const double *__restrict__ edg
 
 template <bool HAS_RDF, bool HAS_CN, bool SMEM_HIST>
 __global__ void __launch_bounds__(PAIR_TILE, 2) k_pair(PairArgs a) {
+    if (a.n_hard && *a.n_hard == 0) return;   // clean-up launch behind the tiled kernel with nothing to clean up
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: edge2[nbins+1] (f64) | cn_thr2[nkeys] (f64) | hist[nkeys*nbins] (u32) | cn_cnt[nkeys] (u32) | keyidx[S*S] (u16)
     double *s_edge2 = reinterpret_cast<double *>(smem_raw);
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(PAIR_TILE, 2) k_pair(PairArgs a) {
             const int si = (int)(me.s & 0xff);
             const int c0 = (int)((me.s >> 8) & 0xfff), c1 = (int)((me.s >> 20) & 0xfff), c2 = (int)((me.s >> 32) & 0xfff);
             const int nc0 = s_geom.nc[0], nc1 = s_geom.nc[1], nc2 = s_geom.nc[2];
-            const int m0 = s_geom.m[0], m1 = s_geom.m[1], m2 = s_geom.m[2];
+            const int m0 = (a.hard_mask && !a.hard_mask[s_geom.cs_off + (c0 * nc1 + c1) * nc2 + c2]) ? -1 : s_geom.m[0];
+            const int m1 = s_geom.m[1], m2 = s_geom.m[2];
             const uint16_t *krow = s_key + si * S;
             for (int d0 = 0; d0 <= m0; ++d0) {
                 const int t0 = c0 + d0, s0 = floordiv_i(t0, nc0), q0 = t0 - s0 * nc0;

@@ -1,0 +1,301 @@
+// pair_tiled.cuh -- the production RDF(+CN) pair kernel: linked-cell tiles staged in shared memory.
+//
+// The generic kernel of pair.cuh reads every candidate atom through L1/L2 once per home atom; at 10 A the candidate
+// set of a 256-atom tile (~200 KB) does not fit in L1, so it runs at L2 speed.  Here a block owns a HOME TILE = a run
+// of `zlen` consecutive cells of one column along the fastest cell axis, and first copies the tile's whole half
+// stencil -- R rows (neighbour columns) x (zlen + 2*m2) virtual cells -- into shared memory, cell by cell, so that
+// each row is one contiguous run ordered by virtual cell.  Every candidate is then read from shared memory.
+//
+//   k_pair_plan   one thread per column: greedy split of the column into tiles whose staged atoms fit `cap`;
+//                 cells too dense even alone are split by rows, or marked "hard" and left to the generic kernel.
+//   k_pair_tiled  persistent blocks over the tile list.  Work item = (home cell, row); a warp takes one item:
+//                 lanes = (home atom i, sub-lane s) with G = 32 / n_home sub-lanes per home atom striding the
+//                 candidate run, so control flow is warp-uniform and shared-memory reads are G-way contiguous.
+//
+// Arithmetic, thresholds, folding of species pairs and histogram privatisation are exactly those of pair.cuh.
+#pragma once
+#include "pair.cuh"
+
+#define TILE_THREADS 256
+#define TILE_MAX_ENTRIES 1024     // rows x virtual cells per tile
+
+struct PairTile {
+    int frame, c0, c1, z0, zlen, rb, re, pad;
+};
+
+struct PlanArgs {
+    const FrameGeom *geom;
+    const uint32_t *cell_start;
+    PairTile *tiles;
+    int *n_tiles;            // [0] tiles, [1] hard cells
+    int *flags;              // sticky: bit 0 = tile list overflow
+    uint8_t *hard;           // batch-wide per-cell mask
+    int n_frames, cap, max_tiles;
+};
+
+__device__ __forceinline__ int tile_rows(const FrameGeom &g) { return (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1); }
+
+__device__ __forceinline__ void tile_row_offset(const FrameGeom &g, int r, int &d0, int &d1) {
+    if (r <= g.m[1]) { d0 = 0; d1 = r; }
+    else {
+        const int rr = r - (g.m[1] + 1), w = 2 * g.m[1] + 1;
+        d0 = 1 + rr / w;
+        d1 = rr - (d0 - 1) * w - g.m[1];
+    }
+}
+
+// atoms in the virtual cells [va, vb] of the column starting at cs[colbase]
+__device__ __forceinline__ int column_count(const uint32_t *cs, int colbase, int nc2, int va, int vb) {
+    const int total = (int)(cs[colbase + nc2] - cs[colbase]);
+    const int fa = floordiv_i(va, nc2), fb = floordiv_i(vb + 1, nc2);
+    const int qa = va - fa * nc2, qb = vb + 1 - fb * nc2;
+    return (fb - fa) * total + (int)cs[colbase + qb] - (int)cs[colbase + qa];
+}
+
+__global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
+    // thread -> (frame, column)
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int f = 0;
+    // frames may have different grids: walk the frames (n_frames is small next to the thread count)
+    for (; f < a.n_frames; ++f) {
+        long long cols = (long long)a.geom[f].nc[0] * a.geom[f].nc[1];
+        if (t < cols) break;
+        t -= cols;
+    }
+    if (f >= a.n_frames) return;
+    const FrameGeom &g = a.geom[f];
+    const uint32_t *cs = a.cell_start + g.cs_off;
+    const int nc1 = g.nc[1], nc2 = g.nc[2], m2 = g.m[2];
+    const int c0 = (int)(t / nc1), c1 = (int)(t - (long long)c0 * nc1);
+    const int R = tile_rows(g);
+    const int vmax = TILE_MAX_ENTRIES / R;          // virtual cells per row that the offset table can hold
+    const int homebase = (c0 * nc1 + c1) * nc2;
+    int z = 0;
+    while (z < nc2) {
+        int zlen = min(nc2 - z, vmax - 2 * m2);
+        if (zlen < 1) zlen = 1;                     // host guarantees vmax >= 2*m2 + 1
+        int total = 0;
+        for (;;) {
+            total = 0;
+            for (int r = 0; r < R; ++r) {
+                int d0, d1;
+                tile_row_offset(g, r, d0, d1);
+                const int t0 = c0 + d0, t1 = c1 + d1;
+                const int q0 = t0 - floordiv_i(t0, g.nc[0]) * g.nc[0], q1 = t1 - floordiv_i(t1, nc1) * nc1;
+                total += column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + zlen - 1 + m2);
+            }
+            if (total <= a.cap || zlen == 1) break;
+            --zlen;
+        }
+        const int home = (int)(cs[homebase + z + zlen] - cs[homebase + z]);
+        if (home > 0) {
+            if (total <= a.cap) {
+                int k = atomicAdd(&a.n_tiles[0], 1);
+                if (k < a.max_tiles) a.tiles[k] = PairTile{f, c0, c1, z, zlen, 0, R, 0};
+                else atomicOr(a.flags, 1);
+            } else {
+                // a single home cell whose stencil does not fit: split by rows; a row that does not fit alone -> hard cell
+                bool hard = false;
+                for (int r = 0; r < R && !hard; ++r) {
+                    int d0, d1;
+                    tile_row_offset(g, r, d0, d1);
+                    const int t0 = c0 + d0, t1 = c1 + d1;
+                    const int q0 = t0 - floordiv_i(t0, g.nc[0]) * g.nc[0], q1 = t1 - floordiv_i(t1, nc1) * nc1;
+                    if (column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + m2) > a.cap) hard = true;
+                }
+                if (hard) {
+                    a.hard[g.cs_off + homebase + z] = 1;
+                    atomicAdd(&a.n_tiles[1], 1);
+                } else {
+                    int rb = 0;
+                    while (rb < R) {
+                        int acc = 0, re = rb;
+                        while (re < R) {
+                            int d0, d1;
+                            tile_row_offset(g, re, d0, d1);
+                            const int t0 = c0 + d0, t1 = c1 + d1;
+                            const int q0 = t0 - floordiv_i(t0, g.nc[0]) * g.nc[0], q1 = t1 - floordiv_i(t1, nc1) * nc1;
+                            const int c = column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + m2);
+                            if (acc + c > a.cap) break;
+                            acc += c;
+                            ++re;
+                        }
+                        int k = atomicAdd(&a.n_tiles[0], 1);
+                        if (k < a.max_tiles) a.tiles[k] = PairTile{f, c0, c1, z, 1, rb, re, 0};
+                        else atomicOr(a.flags, 1);
+                        rb = re;
+                    }
+                }
+            }
+        }
+        z += zlen;
+    }
+}
+
+struct TiledArgs {
+    PairArgs p;
+    const PairTile *tiles;
+    const int *n_tiles;
+    int cap;                 // staged atoms per tile
+    int max_tiles;
+};
+
+template <bool HAS_CN>
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_pair_tiled(TiledArgs ta) {
+    const PairArgs &a = ta.p;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: atoms[cap] (32 B) | edge2[nbins+1] | cn_thr2[nkeys] | hist[nkeys*nbins] u32 | cn_cnt[nkeys] u32 | off[ENTRIES+1] int | keyidx[S*S] u16
+    SAtom *s_atoms = reinterpret_cast<SAtom *>(smem_raw);
+    double *s_edge2 = reinterpret_cast<double *>(s_atoms + ta.cap);
+    double *s_cnthr = s_edge2 + a.nbins + 1;
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_cnthr + (HAS_CN ? a.nkeys : 0));
+    uint32_t *s_cn = s_hist + a.nkeys * a.nbins;
+    int *s_off = reinterpret_cast<int *>(s_cn + (HAS_CN ? a.nkeys : 0));
+    uint16_t *s_key = reinterpret_cast<uint16_t *>(s_off + TILE_MAX_ENTRIES + 1);
+    __shared__ FrameGeom s_geom;
+    __shared__ PairTile s_tile;
+
+    const int S = a.n_species;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = TILE_THREADS / 32;
+    for (int k = threadIdx.x; k <= a.nbins; k += blockDim.x) s_edge2[k] = a.edge2[k];
+    for (int k = threadIdx.x; k < a.nkeys * a.nbins; k += blockDim.x) s_hist[k] = 0u;
+    if (HAS_CN)
+        for (int k = threadIdx.x; k < a.nkeys; k += blockDim.x) { s_cnthr[k] = a.cn_thr2[k]; s_cn[k] = 0u; }
+    for (int k = threadIdx.x; k < S * S; k += blockDim.x) s_key[k] = a.keyidx[k];
+
+    const int n_tiles = min(*ta.n_tiles, ta.max_tiles);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();     // previous tile fully consumed (atoms, offsets, cn counters)
+        if (threadIdx.x < 8) reinterpret_cast<int *>(&s_tile)[threadIdx.x] = reinterpret_cast<const int *>(&ta.tiles[tile])[threadIdx.x];
+        __syncthreads();
+        const int f = s_tile.frame;
+        if (threadIdx.x < (int)(sizeof(FrameGeom) / sizeof(int)))
+            reinterpret_cast<int *>(&s_geom)[threadIdx.x] = reinterpret_cast<const int *>(&a.geom[f])[threadIdx.x];
+        __syncthreads();
+        const SAtom *fr = a.sorted + (long long)f * a.n_atoms;
+        const uint32_t *cs = a.cell_start + s_geom.cs_off;
+        const int nc0 = s_geom.nc[0], nc1 = s_geom.nc[1], nc2 = s_geom.nc[2];
+        const int m2 = s_geom.m[2];
+        const int c0 = s_tile.c0, c1 = s_tile.c1, z0 = s_tile.z0, zlen = s_tile.zlen, rb = s_tile.rb;
+        const int RR = s_tile.re - rb;              // rows staged
+        const int V = zlen + 2 * m2;                // virtual cells per row
+        const int E = RR * V;
+
+        // ---- stage: offsets (warp 0 scans the entry populations), then one warp per entry copies its cell ----
+        if (warp == 0) {
+            int carry = 0;
+            for (int e0 = 0; e0 < E; e0 += 32) {
+                const int e = e0 + lane;
+                int cnt = 0;
+                if (e < E) {
+                    const int r = rb + e / V, v = e - (e / V) * V;
+                    int d0, d1;
+                    tile_row_offset(s_geom, r, d0, d1);
+                    const int t0 = c0 + d0, t1 = c1 + d1, t2 = z0 - m2 + v;
+                    const int q0 = t0 - floordiv_i(t0, nc0) * nc0, q1 = t1 - floordiv_i(t1, nc1) * nc1, q2 = t2 - floordiv_i(t2, nc2) * nc2;
+                    const int cell = (q0 * nc1 + q1) * nc2 + q2;
+                    cnt = (int)(cs[cell + 1] - cs[cell]);
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (e < E) s_off[e] = carry + incl - cnt;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_off[E] = carry;
+        }
+        __syncthreads();
+        for (int e = warp; e < E; e += nwarp) {
+            const int r = rb + e / V, v = e - (e / V) * V;
+            int d0, d1;
+            tile_row_offset(s_geom, r, d0, d1);
+            const int t0 = c0 + d0, t1 = c1 + d1, t2 = z0 - m2 + v;
+            const int q0 = t0 - floordiv_i(t0, nc0) * nc0, q1 = t1 - floordiv_i(t1, nc1) * nc1, q2 = t2 - floordiv_i(t2, nc2) * nc2;
+            const int cell = (q0 * nc1 + q1) * nc2 + q2;
+            const int src = (int)cs[cell], n = (int)cs[cell + 1] - src, dst = s_off[e];
+            const double2 *gp = reinterpret_cast<const double2 *>(fr + src);
+            double2 *sp = reinterpret_cast<double2 *>(s_atoms + dst);
+            for (int k = lane; k < 2 * n; k += 32) sp[k] = __ldg(gp + k);
+        }
+        __syncthreads();
+
+        // ---- compute: work item = (home cell, staged row) ----
+        const int items = zlen * RR;
+        for (int item = warp; item < items; item += nwarp) {
+            const int hz = item / RR, rr = item - hz * RR, r = rb + rr;
+            const int z = z0 + hz;
+            const int hcell = (c0 * nc1 + c1) * nc2 + z;
+            const int hb = (int)cs[hcell], nh = (int)cs[hcell + 1] - hb;
+            if (nh == 0) continue;
+            int d0, d1;
+            tile_row_offset(s_geom, r, d0, d1);
+            const int t0 = c0 + d0, t1 = c1 + d1;
+            const int s0 = floordiv_i(t0, nc0), s1 = floordiv_i(t1, nc1);
+            const double fs0 = (double)s0, fs1 = (double)s1;
+            const bool home_row = (r == 0);
+            const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // staged position of the home cell itself
+            for (int h0 = 0; h0 < nh; h0 += 32) {
+                const int ng = min(32, nh - h0);                 // home atoms in this group
+                const int G = 32 / ng;
+                const int il = lane / G, sub = lane - il * G;
+                const bool active = il < ng;
+                SAtom me;
+                me.x = me.y = me.z = 0.0; me.s = 0;
+                if (active) me = load_satom(fr + hb + h0 + il);
+                const int ism = own_off + h0 + il;
+                const uint16_t *krow = s_key + (int)(me.s & 0xff) * S;
+                int d2 = home_row ? 0 : -m2;
+                while (d2 <= m2) {
+                    const int t2 = z + d2, s2 = floordiv_i(t2, nc2), q2 = t2 - s2 * nc2;
+                    const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
+                    const int v = hz + m2 + d2;
+                    const int jb = s_off[rr * V + v], je = s_off[rr * V + v + len];
+                    const bool after_me = home_row && d2 == 0;   // own cell leads this run: partners after me only
+                    const double fs2 = (double)s2;
+                    const double Tx = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
+                    const double Ty = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
+                    const double Tz = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
+                    if (active) {
+#pragma unroll 4
+                        for (int j = jb + sub; j < je; j += G) {
+                            const double2 *q = reinterpret_cast<const double2 *>(s_atoms + j);
+                            const double2 o0 = q[0], o1 = q[1];
+                            const double dx = (o0.x - me.x) + Tx;
+                            const double dy = (o0.y - me.y) + Ty;
+                            const double dz = (o1.x - me.z) + Tz;
+                            const double dd = (dx * dx + dy * dy) + dz * dz;
+                            if (dd < a.r2search && !(after_me && j <= ism)) {
+                                const int key = krow[(int)(__double_as_longlong(o1.y) & 0xff)];
+                                if (dd < a.r2max) {
+                                    const int b = rdf_bin(dd, s_edge2, a.inv_dr_f, a.nbins);
+                                    atomicAdd(&s_hist[key * a.nbins + b], 1u);
+                                }
+                                if (HAS_CN && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
+                            }
+                        }
+                    }
+                    d2 += len;
+                }
+            }
+        }
+        if (HAS_CN) {
+            __syncthreads();
+            for (int k = threadIdx.x; k < a.nkeys; k += blockDim.x) {
+                const uint32_t v = s_cn[k];
+                if (v) {
+                    atomicAdd(&a.cn_out[(size_t)f * a.nkeys + k], (unsigned long long)v);
+                    s_cn[k] = 0u;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long *slab = a.slabs + (size_t)blockIdx.x * a.nkeys * a.nbins;
+    for (int k = threadIdx.x; k < a.nkeys * a.nbins; k += blockDim.x) {
+        const uint32_t v = s_hist[k];
+        if (v) slab[k] += v;
+    }
+}

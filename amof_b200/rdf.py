@@ -108,6 +108,14 @@ class Rdf(object):
     def compute_rdf(self, trajectory, dr, rmax, distributed=None):
         atomic_numbers_unique = list(set(trajectory[0].get_atomic_numbers()))   # column order, SURVEY.md Q3
 
+        rmax, bins, r = self._axis(trajectory, dr, rmax)      # half-cell clamp; int(rmax // dr) bins (Q1); r = arange(bins)*dr
+        logger.info("Start computing rdf for %s frames with dr = %s and rmax = %s", len(trajectory), dr, rmax)
+        zs, spec, res = pair_histograms(trajectory, float(rmax), bins, distributed=distributed)
+        self._assemble(atomic_numbers_unique, zs, spec, res, r, rmax)
+
+    @staticmethod
+    def _axis(trajectory, dr, rmax):
+        """(rmax after the half-cell rule, bins, r) exactly as compute_rdf derives them (rdf.py:74-83)."""
         rmax_half_cell = _half_cell_rmax(trajectory)
         if isinstance(rmax, str):
             if rmax != 'half_cell':
@@ -116,14 +124,13 @@ class Rdf(object):
         elif rmax > rmax_half_cell:
             logger.info("Specified rmax %s is larger than half cell; will use half_cell rmax", rmax)
             rmax = rmax_half_cell
-
-        logger.info("Start computing rdf for %s frames with dr = %s and rmax = %s", len(trajectory), dr, rmax)
-        bins = int(rmax // dr)                      # float floor division, SURVEY.md Q1 (10 // 0.01 == 999)
-        r = np.arange(bins) * dr                    # labelled with the caller's dr, as the reference does
+        bins = int(rmax // dr)
         if bins < 1:
             raise ValueError("rmax // dr gives no bin (rmax = %s, dr = %s)" % (rmax, dr))
+        return rmax, bins, np.arange(bins) * dr
 
-        zs, spec, res = pair_histograms(trajectory, float(rmax), bins, distributed=distributed)
+    def _assemble(self, atomic_numbers_unique, zs, spec, res, r, rmax):
+        """counts -> the reference's DataFrame (rdf.py:95-114)."""
         hist, n_frames = res["hist"], res["n_frames"]
         n_atoms = len(spec)
         volume_mean = res["volume_sum"] / n_frames
@@ -156,6 +163,25 @@ class Rdf(object):
     def get_coordination_number(self, nn_set, cutoff, density):
         """coordination number of the pair ``nn_set`` (e.g. 'Zn-N') by integrating g(r) up to ``cutoff``"""
         return get_coordination_number(self.data['r'], self.data[nn_set], cutoff, density)
+
+
+def rdf_and_cn(trajectory, nb_set_and_cutoff, dr=0.01, rmax='half_cell', delta_Step=1, first_frame=0, distributed=None):
+    """One pass over the trajectory for both ``Rdf.from_trajectory(trajectory, dr, rmax)`` and
+    ``amof_b200.cn.CoordinationNumber.from_trajectory(trajectory, nb_set_and_cutoff, delta_Step, first_frame)``:
+    the pair kernel fills the RDF histograms and the per-frame cutoff counts from the same distances, so the frames
+    cross PCIe once.  Returns (Rdf, CoordinationNumber) identical to the two separate calls."""
+    from . import atom as amatom
+    from . import cn as _cn
+    rdf_class = Rdf()
+    atomic_numbers_unique = list(set(trajectory[0].get_atomic_numbers()))
+    rmax, bins, r = Rdf._axis(trajectory, dr, rmax)
+    cutoff_dict = amatom.format_cutoff(nb_set_and_cutoff)
+    zs, spec, res = pair_histograms(trajectory, float(rmax), bins, cn_cutoff=cutoff_dict, distributed=distributed)
+    rdf_class._assemble(atomic_numbers_unique, zs, spec, res, r, rmax)
+    cn_class = _cn.CoordinationNumber()
+    step = construct_step(delta_Step=delta_Step, first_frame=first_frame, number_of_frames=len(trajectory))
+    cn_class._assemble(nb_set_and_cutoff, step, zs, spec, res["cn"], len(trajectory))
+    return rdf_class, cn_class
 
 
 def _simpson_avg(y, x):

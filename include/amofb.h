@@ -61,6 +61,11 @@ int64_t amofb_launch_count(const amofb_ctx *ctx);
 int amofb_set_profiling(amofb_ctx *ctx, int enabled);
 int amofb_pair_kernel_time(amofb_ctx *ctx, double *total_ms, int64_t *launches, int reset);
 
+/* Device-side stopwatch for benchmarks: amofb_timer_mark records CUDA event `slot` (0..7) on the compute stream,
+ * amofb_timer_elapsed waits for both events and returns the milliseconds between them. */
+int amofb_timer_mark(amofb_ctx *ctx, int slot);
+int amofb_timer_elapsed(amofb_ctx *ctx, int from_slot, int to_slot, double *ms);
+
 /* Page-locked host buffers for callers that want zero-copy streaming (bench.py, the Python classes). */
 int amofb_host_alloc(amofb_ctx *ctx, uint64_t bytes, void **out);
 int amofb_host_free(amofb_ctx *ctx, void *ptr);

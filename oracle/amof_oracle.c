@@ -331,6 +331,27 @@ int orc_cn_frame(int n, const double *pos, const double *cell, const uint8_t *sp
     return visit_pairs(method, n, pos, cell, rc, cn_cb, &c);
 }
 
+/* counts[nframes][nspec][nspec]; frames split across OpenMP threads like joblib splits them (amof/cn.py:78-80). */
+int orc_cn_traj(int nframes, int n, const double *pos, const double *cell, const uint8_t *spec, int nspec,
+                const double *cutoff, int method, int threads, uint64_t *counts) {
+    int rc_all = ORC_OK;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 1 ? threads : 1)
+#endif
+    for (int f = 0; f < nframes; ++f) {
+        int rc = orc_cn_frame(n, pos + 3 * (size_t)n * f, cell + 9 * (size_t)f, spec, nspec, cutoff, method,
+                              counts + (size_t)f * nspec * nspec);
+        if (rc) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+            rc_all = rc;
+        }
+    }
+    return rc_all;
+}
+
 /* ------------------------------------------------------------------ BAD (P6, P7) */
 #define ORC_MAX_NB 64
 typedef struct {

@@ -32,6 +32,7 @@ def lib():
         L.orc_rdf_traj.argtypes = [C.c_int, C.c_int, _dp, _dp, _u8p, C.c_int, C.c_double, C.c_int, C.c_int,
                                    C.c_int, _u64p, _dp]
         L.orc_cn_frame.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, _u64p]
+        L.orc_cn_traj.argtypes = [C.c_int, C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, _u64p]
         L.orc_bad_frame.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.c_int, C.c_int, _u64p, _u64p]
         L.orc_bad_angles.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_long]
@@ -87,6 +88,17 @@ def cn_counts(pos, cell, spec, nspec, cutoff, method=1):
     counts = np.zeros((nspec, nspec), dtype=np.uint64)
     _check(lib().orc_cn_frame(len(spec), pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method,
                               counts.ctypes.data_as(_u64p)), "cn_frame")
+    return counts
+
+
+def cn_traj(pos, cell, spec, nspec, cutoff, method=1, threads=1):
+    """pos[T][n][3] -> uint64 counts[T][nspec][nspec]"""
+    pos, pp = _d(pos); cell, cp = _d(cell); cutoff, kp = _d(cutoff)
+    spec = np.ascontiguousarray(spec, dtype=np.uint8)
+    T, n = pos.shape[0], pos.shape[1]
+    counts = np.zeros((T, nspec, nspec), dtype=np.uint64)
+    _check(lib().orc_cn_traj(T, n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, int(threads),
+                             counts.ctypes.data_as(_u64p)), "cn_traj")
     return counts
 
 

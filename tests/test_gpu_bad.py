@@ -82,6 +82,6 @@ def test_collinear_and_degenerate_angles(backend):
 
 def test_cutoff_precondition(backend):
     pos, cell, spec = random_box(7, 50, 2, False, 6.0)
-    cut = np.full((2, 2), 3.5)      # above half the cell height
+    cut = np.full((2, 2), 4.5)      # above half the cell height (cell edges are 6.0 .. 7.8)
     with pytest.raises(ValueError):
         backend.bad_counts(spec, 2, [(pos[None], cell[None])], cut, [(0, 1)], 0.05, 3600)

@@ -132,3 +132,21 @@ def test_empty_and_errors(backend):
     # the context is still usable afterwards
     ok = backend.pair_counts(spec, 2, [(pos[None], cell[None])], rmax=4.0, nbins=40)
     assert np.array_equal(ok["hist"], orc.rdf_hist(pos, cell, spec, 2, 4.0, 40))
+
+
+@pytest.mark.parametrize("env", [{"AMOFB_PAIR_GENERIC": "1"}, {"AMOFB_TILE_CAP": "256"}, {"AMOFB_TILE_CAP": "300", "AMOFB_CELL_DIV": "1"},
+                                 {"AMOFB_CELL_DIV": "3"}, {"AMOFB_TILE_BLOCKS_PER_SM": "1"}])
+def test_kernel_variants_agree(backend, monkeypatch, env):
+    """Generic kernel, tiled kernel with tiny staging capacity (row-split tiles and 'hard' cells handed to the
+    generic kernel), other cell sizes: all must give the oracle's integers."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    S = 3
+    # a dense blob inside a dilute box makes some home cells exceed a small staging capacity
+    pos, cell, spec = random_box(61, 1500, S, True, 24.0)
+    rng = np.random.default_rng(3)
+    pos[:500] = pos[0] + rng.normal(scale=1.2, size=(500, 3))
+    cut = np.array([[2.9, 3.3, 0.0], [3.3, 0.0, 4.1], [0.0, 4.1, 2.2]])
+    res = backend.pair_counts(spec, S, [(pos[None], cell[None])], rmax=9.0, nbins=900, cn_cutoff=cut)
+    assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell, spec, S, 9.0, 900))
+    assert np.array_equal(res["cn"][0], orc.cn_counts(pos, cell, spec, S, cut))
