@@ -40,6 +40,8 @@ def build(force=False, verbose=False):
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "-shared",
            "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("AMOFB_NVCC_FLAGS", "").split()
+    cmd[1:1] = extra
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -47,6 +47,7 @@ extern "C" int amofb_create(int device, amofb_ctx **out) {
 static void pair_release(amofb_ctx *ctx);
 static void bad_release(amofb_ctx *ctx);
 static void msd_release(amofb_ctx *ctx);
+static void pool_destroy(amofb_ctx *ctx);
 
 extern "C" int amofb_destroy(amofb_ctx *ctx) {
     if (!ctx) return AMOFB_ERR_ARG;
@@ -57,6 +58,7 @@ extern "C" int amofb_destroy(amofb_ctx *ctx) {
     msd_release(ctx);
     for (auto &p : ctx->pending_pair_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto &t : ctx->timer) if (t) cudaEventDestroy(t);
+    pool_destroy(ctx);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     delete ctx;
@@ -171,16 +173,66 @@ extern "C" int amofb_memcpy_d2h(amofb_ctx *ctx, void *dst_host, const void *src_
     return AMOFB_OK;
 }
 
+static int pool_get(amofb_ctx *ctx, void **out, size_t bytes, bool pinned) {
+    *out = nullptr;
+    if (bytes < 256) bytes = 256;
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool_idle.size(); ++i) {
+        const PoolBlock &b = ctx->pool_idle[i];
+        if (b.pinned == pinned && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 &&
+            (best < 0 || b.bytes < ctx->pool_idle[best].bytes))
+            best = i;
+    }
+    PoolBlock blk;
+    if (best >= 0) {
+        blk = ctx->pool_idle[best];
+        ctx->pool_idle.erase(ctx->pool_idle.begin() + best);
+    } else {
+        blk.bytes = bytes;
+        blk.pinned = pinned;
+        cudaError_t e = pinned ? cudaHostAlloc(&blk.p, bytes, cudaHostAllocDefault) : cudaMalloc(&blk.p, bytes);
+        if (e == cudaErrorMemoryAllocation) {
+            // give idle blocks back to the driver and retry once
+            cudaGetLastError();
+            for (auto &b : ctx->pool_idle) { if (b.pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+            ctx->pool_idle.clear();
+            e = pinned ? cudaHostAlloc(&blk.p, bytes, cudaHostAllocDefault) : cudaMalloc(&blk.p, bytes);
+        }
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            return amofb_fail(ctx, AMOFB_ERR_MEMORY, "%s allocation of %zu bytes failed", pinned ? "pinned host" : "device", bytes);
+        }
+        CUDA_TRY(ctx, e);
+    }
+    ctx->pool_live[blk.p] = blk;
+    *out = blk.p;
+    return AMOFB_OK;
+}
+
+// callers make sure no enqueued work still uses p (the release functions synchronise first)
+static void pool_put(amofb_ctx *ctx, void *p) {
+    if (!p) return;
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) return;
+    ctx->pool_idle.push_back(it->second);
+    ctx->pool_live.erase(it);
+}
+
+static void pool_destroy(amofb_ctx *ctx) {
+    for (auto &kv : ctx->pool_live) ctx->pool_idle.push_back(kv.second);
+    ctx->pool_live.clear();
+    for (auto &b : ctx->pool_idle) { if (b.pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+    ctx->pool_idle.clear();
+}
+
 template <typename T>
 static int dev_alloc(amofb_ctx *ctx, T **p, size_t count) {
-    *p = nullptr;
-    cudaError_t e = cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
-    if (e == cudaErrorMemoryAllocation) {
-        cudaGetLastError();
-        return amofb_fail(ctx, AMOFB_ERR_MEMORY, "device allocation of %zu bytes failed", count * sizeof(T));
-    }
-    CUDA_TRY(ctx, e);
-    return AMOFB_OK;
+    return pool_get(ctx, (void **)p, count * sizeof(T), false);
+}
+
+template <typename T>
+static int pinned_alloc(amofb_ctx *ctx, T **p, size_t count) {
+    return pool_get(ctx, (void **)p, count * sizeof(T), true);
 }
 
 static int env_int(const char *name, int dflt) {
@@ -219,16 +271,16 @@ struct Batcher {
     std::vector<unsigned long long> out_all;   // harvested per-frame outputs, frame-major
 };
 
-static void batcher_release(Batcher &b) {
+static void batcher_release(amofb_ctx *ctx, Batcher &b) {
     for (auto &s : b.slot) {
-        cudaFree(s.d_raw); cudaFree(s.d_geom); cudaFreeHost(s.h_geom);
-        cudaFree(s.d_cell_count); cudaFree(s.d_cell_start); cudaFree(s.d_cid); cudaFree(s.d_rank);
-        cudaFree(s.d_sorted); cudaFree(s.d_out); cudaFreeHost(s.h_out);
+        pool_put(ctx, s.d_raw); pool_put(ctx, s.d_geom); pool_put(ctx, s.h_geom);
+        pool_put(ctx, s.d_cell_count); pool_put(ctx, s.d_cell_start); pool_put(ctx, s.d_cid); pool_put(ctx, s.d_rank);
+        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
     }
-    cudaFree(b.d_species);
+    pool_put(ctx, b.d_species);
     b.d_species = nullptr;
 }
 
@@ -248,7 +300,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
     for (auto &s : b.slot) {
         AMOFB_TRY(dev_alloc(ctx, &s.d_raw, na * 3));
         AMOFB_TRY(dev_alloc(ctx, &s.d_geom, (size_t)b.cap_frames));
-        CUDA_TRY(ctx, cudaHostAlloc((void **)&s.h_geom, sizeof(FrameGeom) * b.cap_frames, cudaHostAllocDefault));
+        AMOFB_TRY(pinned_alloc(ctx, &s.h_geom, (size_t)b.cap_frames));
         AMOFB_TRY(dev_alloc(ctx, &s.d_cell_count, b.cells_per_frame * b.cap_frames));
         AMOFB_TRY(dev_alloc(ctx, &s.d_cell_start, b.cells_per_frame * b.cap_frames));
         AMOFB_TRY(dev_alloc(ctx, &s.d_cid, na));
@@ -256,8 +308,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
         AMOFB_TRY(dev_alloc(ctx, &s.d_sorted, na));
         if (per_frame_out > 0) {
             AMOFB_TRY(dev_alloc(ctx, &s.d_out, (size_t)b.cap_frames * per_frame_out));
-            CUDA_TRY(ctx, cudaHostAlloc((void **)&s.h_out, sizeof(unsigned long long) * b.cap_frames * per_frame_out,
-                                        cudaHostAllocDefault));
+            AMOFB_TRY(pinned_alloc(ctx, &s.h_out, (size_t)b.cap_frames * per_frame_out));
         }
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -372,7 +423,8 @@ struct PairState {
     int grid = 0;
     size_t smem = 0;
     double r2search = 0.0, r2max = 0.0;
-    float inv_dr_f = 0.f;
+    float inv_dr_f = 0.f, bin_margin = 0.f;
+    double cn_r2max = 0.0;
     // tiled path (pair_tiled.cuh)
     bool tiled = false;
     PairTile *d_tiles = nullptr;
@@ -387,9 +439,9 @@ static void pair_release(amofb_ctx *ctx) {
     if (!p) return;
     cudaStreamSynchronize(ctx->s_copy);
     cudaStreamSynchronize(ctx->s_compute);
-    batcher_release(p->bt);
-    cudaFree(p->d_edge2); cudaFree(p->d_cnthr2); cudaFree(p->d_keyidx); cudaFree(p->d_slabs); cudaFree(p->d_hist);
-    cudaFree(p->d_tiles); cudaFree(p->d_ntiles); cudaFree(p->d_flags); cudaFree(p->d_hard);
+    batcher_release(ctx, p->bt);
+    pool_put(ctx, p->d_edge2); pool_put(ctx, p->d_cnthr2); pool_put(ctx, p->d_keyidx); pool_put(ctx, p->d_slabs); pool_put(ctx, p->d_hist);
+    pool_put(ctx, p->d_tiles); pool_put(ctx, p->d_ntiles); pool_put(ctx, p->d_flags); pool_put(ctx, p->d_hard);
     delete p;
     ctx->pair = nullptr;
 }
@@ -455,6 +507,9 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
         }
         p->r2max = edge2[nbins];
         p->inv_dr_f = (float)((double)nbins / rmax);
+        // fp32 estimate of d/dr: relative error < 2^-21 (conversion, MUFU.SQRT, multiply, fma) -> absolute < nbins*2^-21
+        double err = (double)nbins * 4.8e-7;
+        p->bin_margin = err < 0.2 ? (float)(2.0 * err + 1e-3) : 0.f;    // 0 = use the searching fallback
     }
     if (p->has_cn)
         for (int a = 0; a < S; ++a)
@@ -463,7 +518,7 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
                 cnthr[fold_key(a, b, S)] = c > 0.0 ? host_threshold(c * c, [&](double t) { return sqrt(t) >= c; }) : 0.0;
             }
     p->r2search = p->r2max;
-    for (double t : cnthr) p->r2search = std::max(p->r2search, t);
+    for (double t : cnthr) { p->r2search = std::max(p->r2search, t); p->cn_r2max = std::max(p->cn_r2max, t); }
     std::vector<uint16_t> keyidx((size_t)S * S);
     for (int a = 0; a < S; ++a)
         for (int b = 0; b < S; ++b) keyidx[a * S + b] = (uint16_t)fold_key(a, b, S);
@@ -494,10 +549,10 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     else rc = pair_configure<false, true, false>(ctx, p);
     if (rc) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_hist, hist_n))) return fail(rc);
-    cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * std::max<size_t>(hist_n, 1));
+    if (hist_n) cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * hist_n);
     // tiled kernel: shared memory = fixed tables + as many staged atoms as still let two blocks share an SM
     if (p->smem_hist && n_atoms > 0 && !env_int("AMOFB_PAIR_GENERIC", 0)) {
-        size_t fixed = smem_full + sizeof(int) * (TILE_MAX_ENTRIES + 1) + 64;
+        size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) + 64;
         int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", 2);
         size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
         size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 512;
@@ -505,6 +560,7 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
         long long cap = per_block > fixed ? (long long)((per_block - fixed) / sizeof(SAtom)) : 0;
         int cap_env = env_int("AMOFB_TILE_CAP", 0);
         if (cap_env > 0 && cap_env < cap) cap = cap_env;
+        if (cap > 2000) cap = 2000;     // run lengths must stay below 2048 (magic-number divisions, 16-bit queue indices)
         if (cap >= 256) {
             p->tile_cap = (int)cap;
             p->tile_smem = fixed + sizeof(SAtom) * (size_t)cap;
@@ -555,7 +611,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
         a.sorted = s->d_sorted; a.geom = s->d_geom; a.cell_start = s->d_cell_start;
         a.edge2 = p->d_edge2; a.cn_thr2 = p->d_cnthr2; a.keyidx = p->d_keyidx;
         a.slabs = p->d_slabs; a.ghist = p->d_hist; a.cn_out = s->d_out;
-        a.r2search = p->r2search; a.r2max = p->r2max; a.inv_dr_f = p->inv_dr_f;
+        a.r2search = p->r2search; a.r2max = p->r2max; a.inv_dr_f = p->inv_dr_f; a.bin_margin = p->bin_margin; a.cn_r2max = p->cn_r2max;
         a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys; a.nbins = p->nbins;
         a.tiles_per_frame = (b.n_atoms + PAIR_TILE - 1) / PAIR_TILE;
         a.hard_mask = nullptr; a.n_hard = nullptr;

@@ -17,9 +17,9 @@ static void bad_release(amofb_ctx *ctx) {
     if (!p) return;
     cudaStreamSynchronize(ctx->s_copy);
     cudaStreamSynchronize(ctx->s_compute);
-    batcher_release(p->bt);
-    cudaFree(p->d_cnthr2); cudaFree(p->d_tthr); cudaFree(p->d_keyidx); cudaFree(p->d_triples);
-    cudaFree(p->d_hist); cudaFree(p->d_dropped); cudaFree(p->d_flags);
+    batcher_release(ctx, p->bt);
+    pool_put(ctx, p->d_cnthr2); pool_put(ctx, p->d_tthr); pool_put(ctx, p->d_keyidx); pool_put(ctx, p->d_triples);
+    pool_put(ctx, p->d_hist); pool_put(ctx, p->d_dropped); pool_put(ctx, p->d_flags);
     delete p;
     ctx->bad = nullptr;
 }

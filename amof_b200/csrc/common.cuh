@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/amofb.h"
@@ -24,8 +25,18 @@ struct PairState;
 struct BadState;
 struct MsdState;
 
+// Buffers released by an analysis are kept by the context and handed to the next one: begin/finish pairs run once
+// per trajectory pass, and cudaMalloc / cudaHostAlloc / cudaFree each cost more than a whole batch of kernels.
+struct PoolBlock {
+    void *p;
+    size_t bytes;
+    bool pinned;
+};
+
 struct amofb_ctx {
     int device = 0;
+    std::vector<PoolBlock> pool_idle;
+    std::unordered_map<void *, PoolBlock> pool_live;
     cudaStream_t s_compute = nullptr;
     cudaStream_t s_copy = nullptr;
     std::string err;

@@ -20,9 +20,9 @@ static void msd_release(amofb_ctx *ctx) {
     if (!p) return;
     cudaStreamSynchronize(ctx->s_copy);
     cudaStreamSynchronize(ctx->s_compute);
-    cudaFree(p->d_P); cudaFree(p->d_geom); cudaFree(p->d_masses); cudaFree(p->d_species); cudaFree(p->d_com);
+    pool_put(ctx, p->d_P); pool_put(ctx, p->d_geom); pool_put(ctx, p->d_masses); pool_put(ctx, p->d_species); pool_put(ctx, p->d_com);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(p->d_stage[i]);
+        pool_put(ctx, p->d_stage[i]);
         if (p->ev_stage[i]) cudaEventDestroy(p->ev_stage[i]);
     }
     delete p;
@@ -158,7 +158,7 @@ static int msd_frame_sums(amofb_ctx *ctx, MsdState *p, const double *d_w, double
     ctx->launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
-    cudaFree(d_partial);
+    pool_put(ctx, d_partial);
     CUDA_TRY(ctx, e);
     return AMOFB_OK;
 }
@@ -224,7 +224,7 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     int grid = std::max(1, std::min(p->n, ctx->num_sms * per_sm));
     int rc = AMOFB_OK;
     if ((rc = dev_alloc(ctx, &d_window, (size_t)n_window))) return rc;
-    if ((rc = dev_alloc(ctx, &d_partial, (size_t)grid * S * n_window))) { cudaFree(d_window); return rc; }
+    if ((rc = dev_alloc(ctx, &d_partial, (size_t)grid * S * n_window))) { pool_put(ctx, d_window); return rc; }
     std::vector<double> part((size_t)grid * S * n_window);
     cudaError_t e = cudaMemcpyAsync(d_window, window, sizeof(int) * n_window, cudaMemcpyHostToDevice, ctx->s_compute);
     if (e == cudaSuccess) {
@@ -235,8 +235,8 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, ctx->s_compute);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
-    cudaFree(d_window);
-    cudaFree(d_partial);
+    pool_put(ctx, d_window);
+    pool_put(ctx, d_partial);
     CUDA_TRY(ctx, e);
     for (int i = 0; i < S * n_window; ++i) {
         double s = 0.0;
@@ -275,8 +275,8 @@ extern "C" int amofb_msd_direct(amofb_ctx *ctx, double *sums) {
         e = cudaMemcpy(sums + (size_t)s * p->T, d_out, sizeof(double) * p->T, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { rc = amofb_fail(ctx, AMOFB_ERR_CUDA, "msd_direct: %s", cudaGetErrorString(e)); break; }
     }
-    cudaFree(d_w);
-    cudaFree(d_out);
+    pool_put(ctx, d_w);
+    pool_put(ctx, d_out);
     return rc;
 }
 

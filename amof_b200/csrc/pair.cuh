@@ -32,14 +32,30 @@ struct PairArgs {
     const int *n_hard;            // optional: number of marked cells (0 -> the launch returns at once)
     double r2search;              // a pair matters iff d2 < r2search
     double r2max;                 // = edge2[nbins]
+    double cn_r2max;              // max of cn_thr2: cheap pre-test before the per-pair threshold
     float inv_dr_f;
+    float bin_margin;             // see rdf_bin
     int n_atoms, n_frames, n_species, nkeys, nbins;
     int tiles_per_frame;
 };
 
-// exact P4 bin of d2 (precondition: d2 < edge2[nbins])
-__device__ __forceinline__ int rdf_bin(double d2, const double *__restrict__ edge2, float inv_dr_f, int nbins) {
-    int b = (int)(sqrtf((float)d2) * inv_dr_f);
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.SQRT, relative error <= 2^-23
+    return r;
+}
+
+// exact P4 bin of d2 (precondition: d2 < edge2[nbins]).
+// The fp32 estimate r*inv_dr is within nbins*2^-21 of the true quotient; subtracting `margin` (> that bound, < 1/2,
+// checked on the host) makes floor() land on the true bin or the one below it, so ONE comparison against the exact
+// threshold of the next bin settles it.  Falls back to a search when the bin count is too large for that argument.
+__device__ __forceinline__ int rdf_bin(double d2, const double *__restrict__ edge2, float inv_dr_f, float margin, int nbins) {
+    if (margin > 0.f) {
+        int b = (int)fmaf(sqrt_approx((float)d2), inv_dr_f, -margin);   // truncation of a value > -1 -> max(floor, 0)
+        b = b > nbins - 1 ? nbins - 1 : b;
+        return b + (d2 >= edge2[b + 1] ? 1 : 0);                        // edge2[nbins] > d2: never overshoots
+    }
+    int b = (int)(sqrt_approx((float)d2) * inv_dr_f);
     b = b > nbins - 1 ? nbins - 1 : b;
     while (d2 < edge2[b]) --b;          // edge2[0] == 0 stops it
     while (d2 >= edge2[b + 1]) ++b;     // edge2[nbins] > d2 stops it
@@ -115,11 +131,11 @@ __global__ void __launch_bounds__(PAIR_TILE, 2) k_pair(PairArgs a) {
                             if (dd < a.r2search) {
                                 const int key = krow[(int)(o.s & 0xff)];
                                 if (HAS_RDF && dd < a.r2max) {
-                                    const int b = rdf_bin(dd, edge2, a.inv_dr_f, a.nbins);
+                                    const int b = rdf_bin(dd, edge2, a.inv_dr_f, a.bin_margin, a.nbins);
                                     if (SMEM_HIST) atomicAdd(&s_hist[key * a.nbins + b], 1u);
                                     else atomicAdd(&a.ghist[(size_t)key * a.nbins + b], 1ull);
                                 }
-                                if (HAS_CN && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
+                                if (HAS_CN && dd < a.cn_r2max && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
                             }
                         }
                         d2 += len;

@@ -16,8 +16,23 @@
 #pragma once
 #include "pair.cuh"
 
-#define TILE_THREADS 256
+#ifndef TILE_THREADS
+#define TILE_THREADS 512     // 2 blocks x 16 warps per SM at <= 64 registers: measured best on B200 (tools/sweep_pair.sh)
+#endif
+#ifndef TILE_MIN_BLOCKS
+#define TILE_MIN_BLOCKS 2
+#endif
+#ifndef TILE_UNROLL
+#define TILE_UNROLL 1
+#endif
+#ifndef TILE_QUEUE
+#define TILE_QUEUE 0
+#endif
+#define TILE_PRAGMA_(x) _Pragma(#x)
+#define TILE_PRAGMA_UNROLL(n) TILE_PRAGMA_(unroll n)
 #define TILE_MAX_ENTRIES 1024     // rows x virtual cells per tile
+#define TILE_MAX_ZLEN 62
+#define TILE_OFF_WORDS (TILE_MAX_ENTRIES + TILE_MAX_ZLEN + 2)   // offsets: entries + home cells + 1
 
 struct PairTile {
     int frame, c0, c1, z0, zlen, rb, re, pad;
@@ -72,7 +87,7 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
     const int homebase = (c0 * nc1 + c1) * nc2;
     int z = 0;
     while (z < nc2) {
-        int zlen = min(nc2 - z, vmax - 2 * m2);
+        int zlen = min(min(nc2 - z, vmax - 2 * m2), TILE_MAX_ZLEN);
         if (zlen < 1) zlen = 1;                     // host guarantees vmax >= 2*m2 + 1
         int total = 0;
         for (;;) {
@@ -84,6 +99,7 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
                 const int q0 = t0 - floordiv_i(t0, g.nc[0]) * g.nc[0], q1 = t1 - floordiv_i(t1, nc1) * nc1;
                 total += column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + zlen - 1 + m2);
             }
+            total += (int)(cs[homebase + z + zlen] - cs[homebase + z]);   // the home cells are staged once more
             if (total <= a.cap || zlen == 1) break;
             --zlen;
         }
@@ -101,7 +117,7 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
                     tile_row_offset(g, r, d0, d1);
                     const int t0 = c0 + d0, t1 = c1 + d1;
                     const int q0 = t0 - floordiv_i(t0, g.nc[0]) * g.nc[0], q1 = t1 - floordiv_i(t1, nc1) * nc1;
-                    if (column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + m2) > a.cap) hard = true;
+                    if (column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + m2) + home > a.cap) hard = true;
                 }
                 if (hard) {
                     a.hard[g.cs_off + homebase + z] = 1;
@@ -109,7 +125,7 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
                 } else {
                     int rb = 0;
                     while (rb < R) {
-                        int acc = 0, re = rb;
+                        int acc = home, re = rb;
                         while (re < R) {
                             int d0, d1;
                             tile_row_offset(g, re, d0, d1);
@@ -140,23 +156,116 @@ struct TiledArgs {
     int max_tiles;
 };
 
+// ---- hit queue -------------------------------------------------------------------------------------------
+// The candidate loop only decides "d2 < r2search" and appends the hits (d2 + who) to a per-warp ring of 64
+// 16-byte entries in shared memory, at warp-aggregated positions (one ballot per iteration).  Whenever 32 hits are
+// waiting, all 32 lanes bin one each: the expensive part (bin search, species-pair lookup, shared atomics) always
+// runs with full warps instead of the ~1/4-full warps a branch inside the loop would leave.
+struct HitQueue {
+    ulonglong2 *q;       // [64]
+    unsigned head, tail; // warp-uniform
+};
+
 template <bool HAS_CN>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_pair_tiled(TiledArgs ta) {
+__device__ __forceinline__ void hits_flush(const PairArgs &a, const SAtom *__restrict__ s_atoms, const double *__restrict__ s_edge2,
+                                           const double *__restrict__ s_cnthr, uint32_t *__restrict__ s_hist, uint32_t *__restrict__ s_cn,
+                                           const uint16_t *__restrict__ s_key, HitQueue &hq, int lane, int count) {
+    __syncwarp();
+    if (lane < count) {
+        const ulonglong2 e = hq.q[(hq.head + lane) & 63u];
+        const double dd = __longlong_as_double((long long)e.x);
+        const int j = (int)(e.y & 0xffffu), hi = (int)(e.y >> 16);
+        const int sj = reinterpret_cast<const unsigned char *>(s_atoms + j)[24];
+        const int si = reinterpret_cast<const unsigned char *>(s_atoms + hi)[24];
+        const int key = s_key[si * a.n_species + sj];
+        if (dd < a.r2max) {
+            const int b = rdf_bin(dd, s_edge2, a.inv_dr_f, a.bin_margin, a.nbins);
+            atomicAdd(&s_hist[key * a.nbins + b], 1u);
+        }
+        if (HAS_CN && dd < a.cn_r2max && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
+    }
+    hq.head += count;
+    __syncwarp();
+}
+
+// One run of staged candidates [jb, je) against the home atoms of this warp: lane (il, sub) takes jb+sub, +G, ...
+//   SHIFT: the run sits in a periodic image (T != 0); without it (pj - pi) + 0 == pj - pi bit for bit, so the adds go.
+//   AFTER: the run starts with the home cell itself: only partners staged after me (index > ism) count.
+template <bool HAS_CN, bool SHIFT, bool AFTER>
+__device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restrict__ s_atoms, const double *__restrict__ s_edge2,
+                                         const double *__restrict__ s_cnthr, uint32_t *__restrict__ s_hist, uint32_t *__restrict__ s_cn,
+                                         const uint16_t *__restrict__ s_key, HitQueue &hq, const SAtom &me, double Tx, double Ty, double Tz,
+                                         int jb, int je, int G, int n_iter, int sub, bool active, int ism, int hidx, int lane,
+                                         unsigned lt_mask) {
+    const double r2search = a.r2search;
+#if TILE_QUEUE
+    const unsigned long long who_hi = (unsigned long long)hidx << 16;
+    int j = jb + sub;
+    TILE_PRAGMA_UNROLL(TILE_UNROLL)
+    for (int k = 0; k < n_iter; ++k, j += G) {
+        const bool valid = active && j < je;
+        const double2 *q = reinterpret_cast<const double2 *>(s_atoms + (valid ? j : jb));
+        const double2 o0 = q[0];
+        const double oz = reinterpret_cast<const double *>(q)[2];
+        double dx = o0.x - me.x, dy = o0.y - me.y, dz = oz - me.z;
+        if (SHIFT) { dx += Tx; dy += Ty; dz += Tz; }
+        const double dd = (dx * dx + dy * dy) + dz * dz;
+        const bool hit = valid && dd < r2search && !(AFTER && j <= ism);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const unsigned pos = (hq.tail + __popc(m & lt_mask)) & 63u;
+            hq.q[pos] = make_ulonglong2((unsigned long long)__double_as_longlong(dd), who_hi | (unsigned long long)j);
+        }
+        hq.tail += __popc(m);
+        if (hq.tail - hq.head >= 32u) hits_flush<HAS_CN>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, lane, 32);
+    }
+#else
+    if (!active) return;
+    const double r2max = a.r2max, cn_r2max = a.cn_r2max;
+    const float inv_dr_f = a.inv_dr_f, margin = a.bin_margin;
+    const int nbins = a.nbins;
+    const uint16_t *krow = s_key + (int)(me.s & 0xff) * a.n_species;
+    TILE_PRAGMA_UNROLL(TILE_UNROLL)
+    for (int j = jb + sub; j < je; j += G) {
+        const double2 *q = reinterpret_cast<const double2 *>(s_atoms + j);
+        const double2 o0 = q[0], o1 = q[1];
+        double dx = o0.x - me.x, dy = o0.y - me.y, dz = o1.x - me.z;
+        if (SHIFT) { dx += Tx; dy += Ty; dz += Tz; }
+        const double dd = (dx * dx + dy * dy) + dz * dz;
+        if (dd < r2search && !(AFTER && j <= ism)) {
+            const int key = krow[(int)(__double_as_longlong(o1.y) & 0xff)];
+            if (dd < r2max) {
+                const int b = rdf_bin(dd, s_edge2, inv_dr_f, margin, nbins);
+                atomicAdd(&s_hist[key * nbins + b], 1u);
+            }
+            if (HAS_CN && dd < cn_r2max && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
+        }
+    }
+#endif
+}
+
+template <bool HAS_CN>
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(TiledArgs ta) {
     const PairArgs &a = ta.p;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: atoms[cap] (32 B) | edge2[nbins+1] | cn_thr2[nkeys] | hist[nkeys*nbins] u32 | cn_cnt[nkeys] u32 | off[ENTRIES+1] int | keyidx[S*S] u16
+    // layout: atoms[cap] (32 B) | edge2[nbins+1] | cn_thr2[nkeys] | hist[nkeys*nbins] u32 | cn_cnt[nkeys] u32 | off[] int | hit queues | keyidx[S*S] u16
     SAtom *s_atoms = reinterpret_cast<SAtom *>(smem_raw);
     double *s_edge2 = reinterpret_cast<double *>(s_atoms + ta.cap);
     double *s_cnthr = s_edge2 + a.nbins + 1;
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_cnthr + (HAS_CN ? a.nkeys : 0));
     uint32_t *s_cn = s_hist + a.nkeys * a.nbins;
     int *s_off = reinterpret_cast<int *>(s_cn + (HAS_CN ? a.nkeys : 0));
-    uint16_t *s_key = reinterpret_cast<uint16_t *>(s_off + TILE_MAX_ENTRIES + 1);
+    ulonglong2 *s_queue = reinterpret_cast<ulonglong2 *>((reinterpret_cast<uintptr_t>(s_off + TILE_OFF_WORDS) + 15) & ~(uintptr_t)15);   // [nwarp][64]
+    uint16_t *s_key = reinterpret_cast<uint16_t *>(s_queue + 64 * (TILE_THREADS / 32));
     __shared__ FrameGeom s_geom;
     __shared__ PairTile s_tile;
 
     const int S = a.n_species;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = TILE_THREADS / 32;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    HitQueue hq;
+    hq.q = s_queue + 64 * warp;
+    hq.head = hq.tail = 0u;
     for (int k = threadIdx.x; k <= a.nbins; k += blockDim.x) s_edge2[k] = a.edge2[k];
     for (int k = threadIdx.x; k < a.nkeys * a.nbins; k += blockDim.x) s_hist[k] = 0u;
     if (HAS_CN)
@@ -181,54 +290,75 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_pair_tiled(TiledArgs ta) {
         const int V = zlen + 2 * m2;                // virtual cells per row
         const int E = RR * V;
 
-        // ---- stage: offsets (warp 0 scans the entry populations), then one warp per entry copies its cell ----
+        // ---- stage ----------------------------------------------------------------------------------------
+        // entries: RR rows x V virtual cells, then the zlen home cells once more (so the compute phase never
+        // touches global memory).  1) every thread fetches populations, 2) warp 0 scans them in shared memory,
+        // 3) one warp per row copies the row: consecutive virtual cells are consecutive in the sorted frame until
+        // the column wraps, so a row is a few long coalesced runs.
+        const int EH = E + zlen;                    // + home entries
+        const int homebase = (c0 * nc1 + c1) * nc2;
+        for (int e = threadIdx.x; e < EH; e += blockDim.x) {
+            int cell;
+            if (e < E) {
+                const int r = rb + e / V, v = e - (e / V) * V;
+                int d0, d1;
+                tile_row_offset(s_geom, r, d0, d1);
+                const int t0 = c0 + d0, t1 = c1 + d1, t2 = z0 - m2 + v;
+                const int q0 = t0 - floordiv_i(t0, nc0) * nc0, q1 = t1 - floordiv_i(t1, nc1) * nc1, q2 = t2 - floordiv_i(t2, nc2) * nc2;
+                cell = (q0 * nc1 + q1) * nc2 + q2;
+            } else cell = homebase + z0 + (e - E);
+            s_off[e + 1] = (int)(cs[cell + 1] - cs[cell]);
+        }
+        __syncthreads();
         if (warp == 0) {
             int carry = 0;
-            for (int e0 = 0; e0 < E; e0 += 32) {
+            for (int e0 = 0; e0 < EH; e0 += 32) {
                 const int e = e0 + lane;
-                int cnt = 0;
-                if (e < E) {
-                    const int r = rb + e / V, v = e - (e / V) * V;
-                    int d0, d1;
-                    tile_row_offset(s_geom, r, d0, d1);
-                    const int t0 = c0 + d0, t1 = c1 + d1, t2 = z0 - m2 + v;
-                    const int q0 = t0 - floordiv_i(t0, nc0) * nc0, q1 = t1 - floordiv_i(t1, nc1) * nc1, q2 = t2 - floordiv_i(t2, nc2) * nc2;
-                    const int cell = (q0 * nc1 + q1) * nc2 + q2;
-                    cnt = (int)(cs[cell + 1] - cs[cell]);
-                }
+                const int cnt = e < EH ? s_off[e + 1] : 0;
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     int t = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += t;
                 }
-                if (e < E) s_off[e] = carry + incl - cnt;
+                __syncwarp();
+                if (e < EH) s_off[e + 1] = carry + incl;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (lane == 0) s_off[E] = carry;
+            if (lane == 0) s_off[0] = 0;
         }
         __syncthreads();
-        for (int e = warp; e < E; e += nwarp) {
-            const int r = rb + e / V, v = e - (e / V) * V;
-            int d0, d1;
-            tile_row_offset(s_geom, r, d0, d1);
-            const int t0 = c0 + d0, t1 = c1 + d1, t2 = z0 - m2 + v;
-            const int q0 = t0 - floordiv_i(t0, nc0) * nc0, q1 = t1 - floordiv_i(t1, nc1) * nc1, q2 = t2 - floordiv_i(t2, nc2) * nc2;
-            const int cell = (q0 * nc1 + q1) * nc2 + q2;
-            const int src = (int)cs[cell], n = (int)cs[cell + 1] - src, dst = s_off[e];
-            const double2 *gp = reinterpret_cast<const double2 *>(fr + src);
-            double2 *sp = reinterpret_cast<double2 *>(s_atoms + dst);
-            for (int k = lane; k < 2 * n; k += 32) sp[k] = __ldg(gp + k);
+        for (int task = warp; task < RR + 1; task += nwarp) {
+            // task < RR: row rb+task, virtual cells [z0-m2, z0+zlen+m2); task == RR: the home cells [z0, z0+zlen)
+            int colbase, va, vb, ebase;
+            if (task < RR) {
+                int d0, d1;
+                tile_row_offset(s_geom, rb + task, d0, d1);
+                const int t0 = c0 + d0, t1 = c1 + d1;
+                const int q0 = t0 - floordiv_i(t0, nc0) * nc0, q1 = t1 - floordiv_i(t1, nc1) * nc1;
+                colbase = (q0 * nc1 + q1) * nc2; va = z0 - m2; vb = z0 + zlen + m2; ebase = task * V;
+            } else { colbase = homebase; va = z0; vb = z0 + zlen; ebase = E; }
+            int v = va;
+            while (v < vb) {                          // one contiguous run per wrap of the column
+                const int q = v - floordiv_i(v, nc2) * nc2;
+                const int run = min(vb - v, nc2 - q);
+                const int src = (int)cs[colbase + q], n = (int)cs[colbase + q + run] - src;
+                const double2 *gp = reinterpret_cast<const double2 *>(fr + src);
+                double2 *sp = reinterpret_cast<double2 *>(s_atoms + s_off[ebase + (v - va)]);
+#pragma unroll 4
+                for (int k = lane; k < 2 * n; k += 32) sp[k] = __ldg(gp + k);
+                v += run;
+            }
         }
         __syncthreads();
 
-        // ---- compute: work item = (home cell, staged row) ----
+        // ---- compute: work item = (home cell, staged row); everything is read from shared memory ----
         const int items = zlen * RR;
+        const unsigned rr_magic = (65536u + (unsigned)RR - 1u) / (unsigned)RR;    // exact x / RR for x < 2048
         for (int item = warp; item < items; item += nwarp) {
-            const int hz = item / RR, rr = item - hz * RR, r = rb + rr;
+            const int hz = (int)(((unsigned)item * rr_magic) >> 16), rr = item - hz * RR, r = rb + rr;
             const int z = z0 + hz;
-            const int hcell = (c0 * nc1 + c1) * nc2 + z;
-            const int hb = (int)cs[hcell], nh = (int)cs[hcell + 1] - hb;
+            const int hb = s_off[E + hz], nh = s_off[E + hz + 1] - hb;      // staged home cell
             if (nh == 0) continue;
             int d0, d1;
             tile_row_offset(s_geom, r, d0, d1);
@@ -236,51 +366,41 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_pair_tiled(TiledArgs ta) {
             const int s0 = floordiv_i(t0, nc0), s1 = floordiv_i(t1, nc1);
             const double fs0 = (double)s0, fs1 = (double)s1;
             const bool home_row = (r == 0);
-            const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // staged position of the home cell itself
+            const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // position of the home cell inside row 0
             for (int h0 = 0; h0 < nh; h0 += 32) {
                 const int ng = min(32, nh - h0);                 // home atoms in this group
                 const int G = 32 / ng;
-                const int il = lane / G, sub = lane - il * G;
+                const unsigned g_magic = (65536u + (unsigned)G - 1u) / (unsigned)G;
+                const int il = (int)(((unsigned)lane * g_magic) >> 16), sub = lane - il * G;
                 const bool active = il < ng;
-                SAtom me;
-                me.x = me.y = me.z = 0.0; me.s = 0;
-                if (active) me = load_satom(fr + hb + h0 + il);
+                const int hidx = hb + h0 + (active ? il : 0);
+                const SAtom me = s_atoms[hidx];
                 const int ism = own_off + h0 + il;
-                const uint16_t *krow = s_key + (int)(me.s & 0xff) * S;
                 int d2 = home_row ? 0 : -m2;
                 while (d2 <= m2) {
                     const int t2 = z + d2, s2 = floordiv_i(t2, nc2), q2 = t2 - s2 * nc2;
                     const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
                     const int v = hz + m2 + d2;
                     const int jb = s_off[rr * V + v], je = s_off[rr * V + v + len];
+                    const int n_iter = (int)(((unsigned)(je - jb + G - 1) * g_magic) >> 16);
                     const bool after_me = home_row && d2 == 0;   // own cell leads this run: partners after me only
-                    const double fs2 = (double)s2;
-                    const double Tx = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
-                    const double Ty = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
-                    const double Tz = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
-                    if (active) {
-#pragma unroll 4
-                        for (int j = jb + sub; j < je; j += G) {
-                            const double2 *q = reinterpret_cast<const double2 *>(s_atoms + j);
-                            const double2 o0 = q[0], o1 = q[1];
-                            const double dx = (o0.x - me.x) + Tx;
-                            const double dy = (o0.y - me.y) + Ty;
-                            const double dz = (o1.x - me.z) + Tz;
-                            const double dd = (dx * dx + dy * dy) + dz * dz;
-                            if (dd < a.r2search && !(after_me && j <= ism)) {
-                                const int key = krow[(int)(__double_as_longlong(o1.y) & 0xff)];
-                                if (dd < a.r2max) {
-                                    const int b = rdf_bin(dd, s_edge2, a.inv_dr_f, a.nbins);
-                                    atomicAdd(&s_hist[key * a.nbins + b], 1u);
-                                }
-                                if (HAS_CN && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
-                            }
-                        }
+                    if ((s0 | s1 | s2) != 0) {
+                        const double fs2 = (double)s2;
+                        const double Tx = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
+                        const double Ty = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
+                        const double Tz = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
+                        if (after_me) scan_run<HAS_CN, true, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        else scan_run<HAS_CN, true, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                    } else {
+                        if (after_me) scan_run<HAS_CN, false, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        else scan_run<HAS_CN, false, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
                     }
                     d2 += len;
                 }
             }
         }
+        // the staged atoms are about to be replaced: bin what is still queued
+        if (hq.tail != hq.head) hits_flush<HAS_CN>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, lane, (int)(hq.tail - hq.head));
         if (HAS_CN) {
             __syncthreads();
             for (int k = threadIdx.x; k < a.nkeys; k += blockDim.x) {
