@@ -425,7 +425,7 @@ def run_ours(args):
 def cpu_baseline(wl, args, frames=None):
     from oracle import c_oracle as orc
     threads = orc.max_threads()
-    frames = frames or {"c2": 64, "c3": 8, "c4": 16}.get(wl.name, 16)
+    frames = frames or {"c2": 2048, "c3": 160, "c4": 192}.get(wl.name, 16)      # ~10-15 s of CPU work on 16 cores
     frames = min(frames, wl.T)
     dt = wl.cpu_sample(threads, frames)
     return {"value": frames / dt, "unit": wl.unit, "cores": threads, "kind": "port",
@@ -499,7 +499,7 @@ def run_reference(args):
         return
     from oracle import c_oracle as orc
     threads = orc.max_threads()
-    sample = {"c2": 64, "c3": 8, "c4": 16}.get(args.workload, 64)
+    sample = {"c2": 1024, "c3": 64, "c4": 96}.get(args.workload, 64)           # one step = a few seconds of CPU work
     if args.workload in ("c2", "c3"):
         wl = PairWorkload(args.workload, sample)
     elif args.workload == "c4":
