@@ -90,36 +90,78 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
     return v;
 }
 
-// one warp per atom; PREPARE subtracts com[k] first (translate(-cg)), UNWRAP does not
-template <bool PREPARE>
-__global__ void __launch_bounds__(256) k_msd_scan(double *__restrict__ P, const MsdGeom *__restrict__ geom,
-                                                  const double *__restrict__ com, int n, int T) {
-    const int lane = threadIdx.x & 31;
+// one warp per atom; PREPARE subtracts com[k] first (translate(-cg)), UNWRAP does not.
+// Per round the warp takes 32*SCAN_F frames: (1) coalesced read of the 768*... contiguous doubles into a padded
+// shared-memory slab, (2) every lane walks ITS SCAN_F consecutive frames serially (wrap P8 + running sum, in place in
+// the slab), (3) one warp scan of the 32 lane totals, (4) coalesced write-back adding each owner lane's offset.
+// One shuffle scan per 256 frames instead of one per 32, and every global access is a full 128-byte line.
+#define SCAN_F 8
+#define SCAN_WARPS 6
+#define SCAN_LANE_STRIDE (3 * SCAN_F + 1)                  // doubles per lane in the slab (+1 pad: conflict-free)
+// FIXED_CELL: every frame has the same cell (NVT runs): the 144-byte geometry is read once into registers instead
+// of once per frame and lane (it would otherwise be 6x the traffic of the positions themselves).
+template <bool PREPARE, bool FIXED_CELL>
+__global__ void __launch_bounds__(32 * SCAN_WARPS) k_msd_scan(double *__restrict__ P, const MsdGeom *__restrict__ geom,
+                                                              const double *__restrict__ com, int n, int T) {
+    __shared__ double s_slab[SCAN_WARPS][32 * SCAN_LANE_STRIDE];
+    __shared__ double s_off[SCAN_WARPS][32][3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *slab = s_slab[wib];
+    MsdGeom g0;
+    if (FIXED_CELL) g0 = geom[0];
     const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long a = warp; a < n; a += nwarps) {
         double *p = P + (size_t)a * T * 3;
-        double cx = 0.0, cy = 0.0, cz = 0.0;      // running sum carried between 32-frame chunks
-        double lx = 0.0, ly = 0.0, lz = 0.0;      // original (shifted) position of the last frame of the previous chunk
-        for (int k0 = 0; k0 < T; k0 += 32) {
-            const int k = k0 + lane;
-            double x = 0.0, y = 0.0, z = 0.0;
-            if (k < T) {
-                x = p[3 * (size_t)k]; y = p[3 * (size_t)k + 1]; z = p[3 * (size_t)k + 2];
-                if (PREPARE) { x -= com[3 * k]; y -= com[3 * k + 1]; z -= com[3 * k + 2]; }
+        double cx = 0.0, cy = 0.0, cz = 0.0;      // running sum carried between rounds
+        double lx = 0.0, ly = 0.0, lz = 0.0;      // (shifted) original position of the last frame of the previous round
+        for (int k0 = 0; k0 < T; k0 += 32 * SCAN_F) {
+            const int nf = min(32 * SCAN_F, T - k0);               // frames in this round
+            const int ne = 3 * nf;
+            const double *src = p + 3 * (size_t)k0;
+            __syncwarp();
+#pragma unroll 4
+            for (int e = lane; e < ne; e += 32) {
+                double v = src[e];
+                if (PREPARE) v -= com[3 * (size_t)k0 + e];
+                slab[e + e / (3 * SCAN_F)] = v;
             }
-            double px = __shfl_up_sync(0xffffffffu, x, 1), py = __shfl_up_sync(0xffffffffu, y, 1), pz = __shfl_up_sync(0xffffffffu, z, 1);
-            if (lane == 0) { px = lx; py = ly; pz = lz; }
-            double dx = 0.0, dy = 0.0, dz = 0.0;
-            if (k < T) {
-                if (k == 0) { dx = x; dy = y; dz = z; }                       // delta_0 = first positions
-                else wrap_disp(geom[k - 1], x - px, y - py, z - pz, dx, dy, dz);   // cell of frame k-1 wraps step k-1 -> k
+            __syncwarp();
+            const int kb = lane * SCAN_F;                          // first frame (within the round) of this lane
+            const int nv = max(0, min(SCAN_F, nf - kb));
+            double *mine = slab + lane * SCAN_LANE_STRIDE;
+            // the original position just before my first frame: last frame of the lane before me / of the previous round
+            double px = lx, py = ly, pz = lz;
+            if (lane > 0 && nv > 0) { const double *q = mine - SCAN_LANE_STRIDE + 3 * (SCAN_F - 1); px = q[0]; py = q[1]; pz = q[2]; }
+            // remember my own last original position before it is overwritten (the next lane read it above; order matters)
+            double ex = 0.0, ey = 0.0, ez = 0.0;
+            if (nv > 0) { ex = mine[3 * (nv - 1)]; ey = mine[3 * (nv - 1) + 1]; ez = mine[3 * (nv - 1) + 2]; }
+            __syncwarp();
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            for (int i = 0; i < nv; ++i) {
+                const double x = mine[3 * i], y = mine[3 * i + 1], z = mine[3 * i + 2];
+                double dx, dy, dz;
+                const int k = k0 + kb + i;
+                if (k == 0) { dx = x; dy = y; dz = z; }                                       // delta_0 = first positions
+                else wrap_disp(FIXED_CELL ? g0 : geom[k - 1], x - px, y - py, z - pz, dx, dy, dz);   // cell of frame k-1 wraps k-1 -> k
+                px = x; py = y; pz = z;
+                sx += dx; sy += dy; sz += dz;
+                mine[3 * i] = sx; mine[3 * i + 1] = sy; mine[3 * i + 2] = sz;
             }
-            double sx = warp_incl_scan(dx, lane) + cx, sy = warp_incl_scan(dy, lane) + cy, sz = warp_incl_scan(dz, lane) + cz;
-            if (k < T) { p[3 * (size_t)k] = sx; p[3 * (size_t)k + 1] = sy; p[3 * (size_t)k + 2] = sz; }
-            const int last = min(31, T - 1 - k0);
-            cx = __shfl_sync(0xffffffffu, sx, last); cy = __shfl_sync(0xffffffffu, sy, last); cz = __shfl_sync(0xffffffffu, sz, last);
-            lx = __shfl_sync(0xffffffffu, x, last); ly = __shfl_sync(0xffffffffu, y, last); lz = __shfl_sync(0xffffffffu, z, last);
+            const double ix = warp_incl_scan(sx, lane), iy = warp_incl_scan(sy, lane), iz = warp_incl_scan(sz, lane);
+            s_off[wib][lane][0] = cx + (ix - sx);                  // everything before this lane
+            s_off[wib][lane][1] = cy + (iy - sy);
+            s_off[wib][lane][2] = cz + (iz - sz);
+            __syncwarp();
+            double *dst = p + 3 * (size_t)k0;
+#pragma unroll 4
+            for (int e = lane; e < ne; e += 32) {
+                const int owner = e / (3 * SCAN_F), c = e % 3;
+                dst[e] = slab[e + owner] + s_off[wib][owner][c];
+            }
+            cx += __shfl_sync(0xffffffffu, ix, 31); cy += __shfl_sync(0xffffffffu, iy, 31); cz += __shfl_sync(0xffffffffu, iz, 31);
+            const int last_lane = (nf - 1) / SCAN_F;               // lane that owns the round's last frame
+            lx = __shfl_sync(0xffffffffu, ex, last_lane); ly = __shfl_sync(0xffffffffu, ey, last_lane); lz = __shfl_sync(0xffffffffu, ez, last_lane);
         }
     }
 }
@@ -169,52 +211,95 @@ __global__ void __launch_bounds__(256) k_msd_sum_groups(const double *__restrict
 }
 
 // ---- window MSD ------------------------------------------------------------------------------------
-// partial[block][S][nw] += sum over the block's atoms of species s, over k = m+1..T-1, of |R_k - R_{k-m}|^2
+// partial[block][S][nw] = sum over the block's atoms of species s, over k = m+1..T-1, of |R_k - R_{k-m}|^2.
+// One atom at a time: its series is staged in shared memory (SoA), a thread takes frames k = tid+1, +blockDim, ...
+// keeps R_k in registers and walks the window lengths, so each pair costs one shared-memory read of R_{k-m}.
+// The per-window sums stay in registers (MSD_NW per pass) across all atoms of one species; they are reduced over the
+// block only when the species changes, in a fixed order, so the result does not depend on scheduling.
+#define MSD_NW 32
+#define MSD_THREADS 512
+
 template <bool SMEM>
-__global__ void __launch_bounds__(512) k_msd_window(const double *__restrict__ P, const uint8_t *__restrict__ species, int n, int T,
-                                                    const int *__restrict__ window, int nw, int S, double *__restrict__ partial) {
+__global__ void __launch_bounds__(MSD_THREADS) k_msd_window(const double *__restrict__ P, const uint8_t *__restrict__ species, int n, int T,
+                                                            const int *__restrict__ window, int nw, int S, double *__restrict__ partial) {
     extern __shared__ double sm[];
-    double *sx = sm, *sy = sm + (SMEM ? T : 0), *sz = sm + (SMEM ? 2 * T : 0);
-    double *s_acc = sm + (SMEM ? 3 * (size_t)T : 0);    // [S][nw] block accumulators
-    double *s_red = s_acc + (size_t)S * nw;             // [warps]
+    double *s_acc = sm + (SMEM ? 3 * (size_t)T + 1 : 0);    // [S][nw] block accumulators (after the staged series)
+    double *s_red = s_acc + (size_t)S * nw;                 // [nwarp][MSD_NW]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = threadIdx.x; i < S * nw; i += blockDim.x) s_acc[i] = 0.0;
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int a_lo = blockIdx.x * per, a_hi = min(n, a_lo + per);
-    for (int a = a_lo; a < a_hi; ++a) {
-        const double *p = P + (size_t)a * T * 3;
-        __syncthreads();
-        if (SMEM)
-            for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) {
-                const double v = p[i];
-                const int k = i / 3, c = i - 3 * k;
-                (c == 0 ? sx : c == 1 ? sy : sz)[k] = v;
-            }
-        __syncthreads();
-        const int sp = species[a];
-        for (int w = 0; w < nw; ++w) {
-            const int m = window[w];
-            double acc = 0.0;
-            if (m >= 0 && m < T)
-                for (int k = m + 1 + threadIdx.x; k < T; k += blockDim.x) {
-                    double dx, dy, dz;
-                    if (SMEM) { dx = sx[k] - sx[k - m]; dy = sy[k] - sy[k - m]; dz = sz[k] - sz[k - m]; }
-                    else {
-                        dx = p[3 * (size_t)k] - p[3 * (size_t)(k - m)];
-                        dy = p[3 * (size_t)k + 1] - p[3 * (size_t)(k - m) + 1];
-                        dz = p[3 * (size_t)k + 2] - p[3 * (size_t)(k - m) + 2];
-                    }
-                    acc += __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
-                }
+    for (int w0 = 0; w0 < nw; w0 += MSD_NW) {
+        int mw[MSD_NW];
+        double acc[MSD_NW];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-            if (lane == 0) s_red[w * nwarp + warp] = acc;
+        for (int w = 0; w < MSD_NW; ++w) {
+            const int m = (w0 + w < nw) ? window[w0 + w] : -1;
+            mw[w] = (m >= 0 && m < T) ? m : T;              // T: no frame pair qualifies
+            acc[w] = 0.0;
         }
-        __syncthreads();
-        for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-            double s = 0.0;
-            for (int q = 0; q < nwarp; ++q) s += s_red[w * nwarp + q];
-            s_acc[sp * nw + w] += s;
+        int cur_sp = -1;
+        for (int a = a_lo; a <= a_hi; ++a) {
+            const int sp = a < a_hi ? (int)species[a] : -2;
+            if (sp != cur_sp) {
+                if (cur_sp >= 0) {                          // species changed (or done): reduce the register sums
+#pragma unroll
+                    for (int w = 0; w < MSD_NW; ++w) {
+                        double v = acc[w];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                        if (lane == 0) s_red[warp * MSD_NW + w] = v;
+                        acc[w] = 0.0;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < MSD_NW && w0 + threadIdx.x < nw) {
+                        double t = 0.0;
+                        for (int q = 0; q < nwarp; ++q) t += s_red[q * MSD_NW + threadIdx.x];
+                        s_acc[cur_sp * nw + w0 + threadIdx.x] += t;
+                    }
+                    __syncthreads();
+                }
+                cur_sp = sp;
+            }
+            if (a >= a_hi) break;
+            const double *p = P + (size_t)a * T * 3;
+            if (SMEM) {
+                __syncthreads();                            // everyone finished the previous atom
+                // stage the series as it is (AoS, frame k at sm[3k..3k+2]): wide loads, 8 in flight per thread, so the
+                // whole 24*T bytes are requested within one memory latency
+                if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+                    double2 *s2 = reinterpret_cast<double2 *>(sm);
+                    const int n2 = (3 * T) >> 1;
+                    for (int i0 = threadIdx.x; i0 < n2; i0 += 8 * MSD_THREADS) {
+                        double2 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (i0 + u * MSD_THREADS < n2) v[u] = __ldg(p2 + i0 + u * MSD_THREADS);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (i0 + u * MSD_THREADS < n2) s2[i0 + u * MSD_THREADS] = v[u];
+                    }
+                    if ((3 * T) & 1) { if (threadIdx.x == 0) sm[3 * T - 1] = p[3 * T - 1]; }
+                } else {
+                    for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) sm[i] = p[i];
+                }
+                __syncthreads();
+            }
+            for (int k = 1 + threadIdx.x; k < T; k += blockDim.x) {
+                double xk, yk, zk;
+                if (SMEM) { xk = sm[3 * k]; yk = sm[3 * k + 1]; zk = sm[3 * k + 2]; }
+                else { xk = p[3 * (size_t)k]; yk = p[3 * (size_t)k + 1]; zk = p[3 * (size_t)k + 2]; }
+                // branch-free over the windows (32 independent chains in flight): a pair that does not qualify
+                // (k - m < 1) reads frame k itself and contributes exactly 0
+#pragma unroll
+                for (int w = 0; w < MSD_NW; ++w) {
+                    const int j0 = k - mw[w];
+                    const int j = j0 >= 1 ? j0 : k;
+                    double dx, dy, dz;
+                    if (SMEM) { dx = xk - sm[3 * j]; dy = yk - sm[3 * j + 1]; dz = zk - sm[3 * j + 2]; }
+                    else { dx = xk - p[3 * (size_t)j]; dy = yk - p[3 * (size_t)j + 1]; dz = zk - p[3 * (size_t)j + 2]; }
+                    acc[w] += __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
+                }
+            }
         }
     }
     __syncthreads();

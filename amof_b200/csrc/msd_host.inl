@@ -10,7 +10,7 @@ struct MsdState {
     double *d_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     int stage_frames = 0, next_stage = 0;
-    bool have_com = false, prepared = false, consumed = false;
+    bool have_com = false, prepared = false, consumed = false, fixed_cell = false;
     std::vector<double> cell;         // host copy [T][9]
     double mass_sum = 0.0;
 };
@@ -54,6 +54,9 @@ extern "C" int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const 
         }
     }
     for (int i = 0; i < n_atoms; ++i) p->mass_sum += masses[i];
+    p->fixed_cell = true;
+    for (int k = 1; k < n_frames && p->fixed_cell; ++k)
+        if (memcmp(cell + 9 * (size_t)k, cell, sizeof(double) * 9) != 0) p->fixed_cell = false;
     if ((rc = dev_alloc(ctx, &p->d_P, (size_t)n_atoms * n_frames * 3))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_geom, (size_t)n_frames))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_masses, (size_t)n_atoms))) return fail(rc);
@@ -131,15 +134,16 @@ extern "C" int amofb_msd_load_device(amofb_ctx *ctx, int first_frame, int count,
 
 static int msd_scan_grid(amofb_ctx *ctx, int n) {
     long long warps = n;
-    long long blocks = (warps + 7) / 8;
-    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)ctx->num_sms * 8));
+    long long blocks = (warps + SCAN_WARPS - 1) / SCAN_WARPS;
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)ctx->num_sms * 4));
 }
 
 extern "C" int amofb_msd_unwrap(amofb_ctx *ctx) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_unwrap"));
     if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_unwrap after the positions were transformed");
-    k_msd_scan<false><<<msd_scan_grid(ctx, p->n), 256, 0, ctx->s_compute>>>(p->d_P, p->d_geom, nullptr, p->n, p->T);
+    if (p->fixed_cell) k_msd_scan<false, true><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, nullptr, p->n, p->T);
+    else k_msd_scan<false, false><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, nullptr, p->n, p->T);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     p->have_com = false;
@@ -197,17 +201,18 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     if (n_window < 0 || (n_window > 0 && (!window || !sums))) return amofb_fail(ctx, AMOFB_ERR_ARG, "bad window arguments");
     if (!p->prepared) {
         if (!p->have_com) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_window needs amofb_msd_set_com first");
-        k_msd_scan<true><<<msd_scan_grid(ctx, p->n), 256, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
+        if (p->fixed_cell) k_msd_scan<true, true><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
+        else k_msd_scan<true, false><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
         ctx->launches += 1;
         CUDA_TRY(ctx, cudaGetLastError());
         p->prepared = true;
     }
     if (n_window == 0) return AMOFB_OK;
-    const int S = p->S, threads = 512, nwarp = threads / 32;
+    const int S = p->S, threads = MSD_THREADS, nwarp = threads / 32;
     int *d_window = nullptr;
     double *d_partial = nullptr;
-    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)n_window * nwarp);
-    size_t smem_full = sizeof(double) * 3 * (size_t)p->T + extra;
+    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)MSD_NW * nwarp);
+    size_t smem_full = sizeof(double) * (3 * (size_t)p->T + 1) + extra;
     size_t budget = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;
     bool use_smem = smem_full <= budget && !env_int("AMOFB_MSD_NO_SMEM", 0);
     size_t smem = use_smem ? smem_full : extra;

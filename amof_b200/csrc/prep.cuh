@@ -34,6 +34,10 @@ struct PrepArgs {
     SAtom *sorted;            // [F*N]
     int n_atoms;
     int n_frames;
+    // optional compaction of "centre" atoms (bond angles): species_flag[s] != 0 -> append the sorted index
+    const uint8_t *species_flag;   // [n_species] or nullptr
+    uint32_t *centres;             // [F*N]
+    int *n_centres;
 };
 
 __device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__restrict__ p, double *pw, int *c) {
@@ -71,7 +75,9 @@ __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
     }
 }
 
-// one block per frame; writes ncell+1 entries (last = number of atoms)
+// one block per frame; writes ncell+1 entries (last = number of atoms).  Each thread scans SCAN_PER consecutive
+// cells serially, the block scans the per-thread totals: ncell / (1024 * SCAN_PER) rounds of three barriers.
+#define SCAN_PER 8
 __global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
@@ -83,9 +89,15 @@ __global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        uint32_t v = (i < n) ? cnt[i] : 0u;
+    for (int base = 0; base < n; base += blockDim.x * SCAN_PER) {
+        const int i0 = base + threadIdx.x * SCAN_PER;
+        uint32_t loc[SCAN_PER];
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; ++k) {
+            loc[k] = (i0 + k < n) ? cnt[i0 + k] : 0u;
+            v += loc[k];
+        }
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -105,11 +117,14 @@ __global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
             warp_sums[lane] = wi - ws;   // exclusive prefix of the warp totals
         }
         __syncthreads();
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_sums[warp] + incl - v;
-        if (i < n) out[i] = excl;
+        uint32_t run = carry_s + warp_sums[warp] + incl - v;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; ++k) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += loc[k];
+        }
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+        if (threadIdx.x == blockDim.x - 1) carry_s = run;
         __syncthreads();
     }
     if (threadIdx.x == 0) out[n] = carry_s;
@@ -131,5 +146,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         // species | c0 << 8 | c1 << 20 | c2 << 32   (nc <= 1024 per axis)
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
+        if (a.species_flag && a.species_flag[a.species[i]])
+            a.centres[atomicAdd(a.n_centres, 1)] = (uint32_t)((long long)f * a.n_atoms + dst);
     }
 }
