@@ -164,6 +164,9 @@ class PairWorkload:
     def step_resident(self):
         res = self.backend.pair_counts(self.spec, len(self.zs), self._device_chunks(), rmax=self.rmax, nbins=self.bins,
                                        cn_cutoff=self.cut)
+        if self.world > 1:      # the one collective of the path: integer all-reduce of the histograms (NCCL)
+            from amof_b200 import _dist
+            self.total_hist = _dist.allreduce_sum(res["hist"])
         self.last = res
         return res
 
@@ -231,6 +234,9 @@ class BadWorkload:
     def step_resident(self):
         hist, dropped, nf = self.backend.bad_counts(self.spec, len(self.zs), self._device_chunks(), self.cut, self.triples,
                                                     self.dtheta, self.nbins)
+        if self.world > 1:
+            from amof_b200 import _dist
+            self.total_hist = _dist.allreduce_sum(hist)
         self.last = {"hist": hist}
         return self.last
 
@@ -309,9 +315,11 @@ class MsdWorkload:
             self.backend.ctx.sync()
 
     def _analyse(self, s):
-        sums = s.com_sums()
+        """atoms are sharded over ranks: the per-frame mass-weighted sums and the window sums are all-reduced"""
+        from amof_b200 import _dist
+        sums = _dist.allreduce_sum(s.com_sums())
         s.set_com(sums[:, :3] / sums[:, 3:4])
-        return s.window(self.window.astype(np.int32))
+        return _dist.allreduce_sum(s.window(self.window.astype(np.int32)))
 
     def step_resident(self):
         # the device-resident leg times load_device (transpose) + COM + prepare + window; generation is outside
@@ -352,6 +360,7 @@ def run_ours(args):
         wl = BadWorkload(args.workload, args.frames)
     else:
         return run_msd(args, backend, rank, world)
+    wl.world = world
     wl.setup(backend)
 
     # ---- device-resident leg -------------------------------------------------------------------
@@ -386,6 +395,10 @@ def run_ours(args):
     barrier_sync(ctx, world)
     e2e_s = max_over_ranks(time.perf_counter() - t1, world)
 
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     frames_total = wl.T * args.steps * world
@@ -426,9 +439,17 @@ def run_ours(args):
     print(json.dumps(out))
 
 
+def host_threads():
+    """threads the CPU arm may use: every core this process is allowed on (torchrun sets OMP_NUM_THREADS=1, which
+    would otherwise silently serialise the OpenMP oracle)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(wl, args, frames=None):
-    from oracle import c_oracle as orc
-    threads = orc.max_threads()
+    threads = host_threads()
     frames = frames or {"c2": 2048, "c3": 160, "c4": 192}.get(wl.name, 16)      # ~10-15 s of CPU work on 16 cores
     frames = min(frames, wl.T)
     dt = wl.cpu_sample(threads, frames)
@@ -469,6 +490,10 @@ def run_msd(args, backend, rank, world):
             raw = wl._analyse(s)
     ctx.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t1, world)
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     frames_total = wl.T * args.steps * world
@@ -501,8 +526,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import c_oracle as orc
-    threads = orc.max_threads()
+    threads = host_threads()
     sample = {"c2": 1024, "c3": 64, "c4": 96}.get(args.workload, 64)           # one step = a few seconds of CPU work
     if args.workload in ("c2", "c3"):
         wl = PairWorkload(args.workload, sample)
