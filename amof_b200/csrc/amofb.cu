@@ -4,6 +4,7 @@
 #include "prep.cuh"
 #include "pair.cuh"
 #include "pair_tiled.cuh"
+#include "pair_warp.cuh"
 #include "bad.cuh"
 #include "msd.cuh"
 
@@ -437,6 +438,10 @@ struct PairState {
     uint8_t *d_hard = nullptr;
     int tile_cap = 0, tile_grid = 0, max_tiles = 0;
     size_t tile_smem = 0, hard_bytes = 0;
+    // warp-streaming path (pair_warp.cuh)
+    bool warp_mode = false;
+    int warp_grid = 0;
+    size_t warp_smem = 0;
 };
 
 static void pair_release(amofb_ctx *ctx) {
@@ -557,7 +562,7 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if (hist_n) cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * hist_n);
     // tiled kernel: shared memory = fixed tables + as many staged atoms as still let two blocks share an SM
     if (p->smem_hist && n_atoms > 0 && !env_int("AMOFB_PAIR_GENERIC", 0)) {
-        size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) + 64;
+        size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + (TILE_QUEUE ? sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) : 0) + 64;
         int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", 2);
         size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
         size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 512;
@@ -589,8 +594,22 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
             } else cudaGetLastError();
         }
     }
+    if (p->smem_hist && n_atoms > 0 && env_int("AMOFB_PAIR_WARP", 0)) {
+        p->warp_smem = smem_full + sizeof(SAtom) * 2 * WCHUNK * (WARP_THREADS / 32) + sizeof(uint32_t) * p->nkeys * (WARP_THREADS / 32) + 64;
+        int per_sm = 0;
+        cudaError_t e1 = p->has_cn
+            ? cudaFuncSetAttribute(k_pair_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->warp_smem)
+            : cudaFuncSetAttribute(k_pair_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->warp_smem);
+        if (e1 == cudaSuccess)
+            e1 = p->has_cn ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_warp<true>, WARP_THREADS, p->warp_smem)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_warp<false>, WARP_THREADS, p->warp_smem);
+        if (e1 == cudaSuccess && per_sm >= 1) {
+            p->warp_mode = true;
+            p->warp_grid = ctx->num_sms * per_sm;
+        } else cudaGetLastError();
+    }
     if (p->smem_hist) {
-        size_t nslab = (size_t)std::max(p->grid, p->tile_grid);
+        size_t nslab = (size_t)std::max(std::max(p->grid, p->tile_grid), p->warp_grid);
         if ((rc = dev_alloc(ctx, &p->d_slabs, hist_n * nslab))) return fail(rc);
         cudaMemset(p->d_slabs, 0, sizeof(unsigned long long) * hist_n * nslab);
     }
@@ -640,6 +659,22 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 if (R > TILE_MAX_ENTRIES || TILE_MAX_ENTRIES / R < 2 * g.m[2] + 1) tiled = false;
                 ncell_total += (size_t)g.ncell + 1;
                 columns += (long long)g.nc[0] * g.nc[1];
+            }
+            if (p->warp_mode) {
+                WarpArgs wa;
+                wa.p = a; wa.total_cells = 0;
+                for (int f = 0; f < nf; ++f) wa.total_cells += s->h_geom[f].ncell;
+                if (p->has_cn) k_pair_warp<true><<<p->warp_grid, WARP_THREADS, p->warp_smem, ctx->s_compute>>>(wa);
+                else k_pair_warp<false><<<p->warp_grid, WARP_THREADS, p->warp_smem, ctx->s_compute>>>(wa);
+                ctx->launches += 1;
+                CUDA_TRY(ctx, cudaGetLastError());
+                if (ctx->profiling) {
+                    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->s_compute));
+                    ctx->pending_pair_events.emplace_back(e0, e1);
+                }
+                AMOFB_TRY(batcher_commit(ctx, b, *s, nf));
+                done += nf;
+                continue;
             }
             if (tiled) {
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles, 0, sizeof(int) * 4, ctx->s_compute));
@@ -713,7 +748,7 @@ extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_co
                 if (flags) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "tile list overflow (extremely inhomogeneous frame); rerun with AMOFB_PAIR_GENERIC=1");
             }
             if (p->smem_hist) {
-                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, std::max(p->grid, p->tile_grid), (int)hist_n, p->d_hist);
+                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, std::max(std::max(p->grid, p->tile_grid), p->warp_grid), (int)hist_n, p->d_hist);
                 ctx->launches += 1;
                 CUDA_TRY(ctx, cudaGetLastError());
             }

@@ -53,9 +53,11 @@ __device__ __forceinline__ int tile_rows(const FrameGeom &g) { return (g.m[1] + 
 __device__ __forceinline__ void tile_row_offset(const FrameGeom &g, int r, int &d0, int &d1) {
     if (r <= g.m[1]) { d0 = 0; d1 = r; }
     else {
-        const int rr = r - (g.m[1] + 1), w = 2 * g.m[1] + 1;
-        d0 = 1 + rr / w;
-        d1 = rr - (d0 - 1) * w - g.m[1];
+        int rr = r - (g.m[1] + 1);
+        const int w = 2 * g.m[1] + 1;
+        d0 = 1;
+        while (rr >= w) { rr -= w; ++d0; }      // d0 <= m0: a couple of steps, cheaper than a division
+        d1 = rr - g.m[1];
     }
 }
 
@@ -249,14 +251,16 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     const PairArgs &a = ta.p;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: atoms[cap] (32 B) | edge2[nbins+1] | cn_thr2[nkeys] | hist[nkeys*nbins] u32 | cn_cnt[nkeys] u32 | off[] int | hit queues | keyidx[S*S] u16
-    SAtom *s_atoms = reinterpret_cast<SAtom *>(smem_raw);
-    double *s_edge2 = reinterpret_cast<double *>(s_atoms + ta.cap);
-    double *s_cnthr = s_edge2 + a.nbins + 1;
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_cnthr + (HAS_CN ? a.nkeys : 0));
-    uint32_t *s_cn = s_hist + a.nkeys * a.nbins;
-    int *s_off = reinterpret_cast<int *>(s_cn + (HAS_CN ? a.nkeys : 0));
-    ulonglong2 *s_queue = reinterpret_cast<ulonglong2 *>((reinterpret_cast<uintptr_t>(s_off + TILE_OFF_WORDS) + 15) & ~(uintptr_t)15);   // [nwarp][64]
-    uint16_t *s_key = reinterpret_cast<uint16_t *>(s_queue + 64 * (TILE_THREADS / 32));
+    // carved by byte offsets from the shared base, so every pointer keeps the shared address space
+    size_t off = 0;
+    SAtom *s_atoms = reinterpret_cast<SAtom *>(smem_raw + off);            off += sizeof(SAtom) * (size_t)ta.cap;
+    double *s_edge2 = reinterpret_cast<double *>(smem_raw + off);          off += sizeof(double) * (size_t)(a.nbins + 1);
+    double *s_cnthr = reinterpret_cast<double *>(smem_raw + off);          off += sizeof(double) * (size_t)(HAS_CN ? a.nkeys : 0);
+    ulonglong2 *s_queue = reinterpret_cast<ulonglong2 *>(smem_raw + off);  off += sizeof(ulonglong2) * (TILE_QUEUE ? 64 * (TILE_THREADS / 32) : 0);
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem_raw + off);       off += sizeof(uint32_t) * (size_t)a.nkeys * a.nbins;
+    uint32_t *s_cn = reinterpret_cast<uint32_t *>(smem_raw + off);         off += sizeof(uint32_t) * (size_t)(HAS_CN ? a.nkeys : 0);
+    int *s_off = reinterpret_cast<int *>(smem_raw + off);                  off += sizeof(int) * TILE_OFF_WORDS;
+    uint16_t *s_key = reinterpret_cast<uint16_t *>(smem_raw + off);
     __shared__ FrameGeom s_geom;
     __shared__ PairTile s_tile;
 
@@ -362,8 +366,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
             if (nh == 0) continue;
             int d0, d1;
             tile_row_offset(s_geom, r, d0, d1);
-            const int t0 = c0 + d0, t1 = c1 + d1;
-            const int s0 = floordiv_i(t0, nc0), s1 = floordiv_i(t1, nc1);
+            int s0, s1, q0_, q1_;
+            wrap_cell(c0 + d0, nc0, s0, q0_);
+            wrap_cell(c1 + d1, nc1, s1, q1_);
             const double fs0 = (double)s0, fs1 = (double)s1;
             const bool home_row = (r == 0);
             const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // position of the home cell inside row 0
@@ -378,7 +383,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
                 const int ism = own_off + h0 + il;
                 int d2 = home_row ? 0 : -m2;
                 while (d2 <= m2) {
-                    const int t2 = z + d2, s2 = floordiv_i(t2, nc2), q2 = t2 - s2 * nc2;
+                    int s2, q2;
+                    wrap_cell(z + d2, nc2, s2, q2);
                     const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
                     const int v = hz + m2 + d2;
                     const int jb = s_off[rr * V + v], je = s_off[rr * V + v + len];

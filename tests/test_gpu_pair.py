@@ -134,7 +134,7 @@ def test_empty_and_errors(backend):
     assert np.array_equal(ok["hist"], orc.rdf_hist(pos, cell, spec, 2, 4.0, 40))
 
 
-@pytest.mark.parametrize("env", [{"AMOFB_PAIR_GENERIC": "1"}, {"AMOFB_TILE_CAP": "256"}, {"AMOFB_TILE_CAP": "300", "AMOFB_CELL_DIV": "1"},
+@pytest.mark.parametrize("env", [{"AMOFB_PAIR_GENERIC": "1"}, {"AMOFB_PAIR_WARP": "1"}, {"AMOFB_PAIR_WARP": "1", "AMOFB_CELL_DIV": "1"}, {"AMOFB_TILE_CAP": "256"}, {"AMOFB_TILE_CAP": "300", "AMOFB_CELL_DIV": "1"},
                                  {"AMOFB_CELL_DIV": "3"}, {"AMOFB_TILE_BLOCKS_PER_SM": "1"}])
 def test_kernel_variants_agree(backend, monkeypatch, env):
     """Generic kernel, tiled kernel with tiny staging capacity (row-split tiles and 'hard' cells handed to the
