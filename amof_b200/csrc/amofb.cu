@@ -562,7 +562,8 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if (hist_n) cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * hist_n);
     // tiled kernel: shared memory = fixed tables + as many staged atoms as still let two blocks share an SM
     if (p->smem_hist && n_atoms > 0 && !env_int("AMOFB_PAIR_GENERIC", 0)) {
-        size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + (TILE_QUEUE ? sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) : 0) + 64;
+        size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + (TILE_QUEUE ? sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) : 0) +
+                       sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32) + 64;
         int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", 2);
         size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
         size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 512;

@@ -51,8 +51,8 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // threshold of the next bin settles it.  Falls back to a search when the bin count is too large for that argument.
 __device__ __forceinline__ int rdf_bin(double d2, const double *__restrict__ edge2, float inv_dr_f, float margin, int nbins) {
     if (margin > 0.f) {
-        int b = (int)fmaf(sqrt_approx((float)d2), inv_dr_f, -margin);   // truncation of a value > -1 -> max(floor, 0)
-        b = b > nbins - 1 ? nbins - 1 : b;
+        // truncation of a value > -1 -> max(floor, 0); d2 < edge2[nbins] and margin > the estimate's error keep it <= nbins-1
+        const int b = (int)fmaf(sqrt_approx((float)d2), inv_dr_f, -margin);
         return b + (d2 >= edge2[b + 1] ? 1 : 0);                        // edge2[nbins] > d2: never overshoots
     }
     int b = (int)(sqrt_approx((float)d2) * inv_dr_f);
