@@ -158,6 +158,33 @@ struct TiledArgs {
     int max_tiles;
 };
 
+// ---- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier ----------------------------------------
+#ifndef TILE_TMA
+#define TILE_TMA 1
+#endif
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+
 // ---- hit queue -------------------------------------------------------------------------------------------
 // The candidate loop only decides "d2 < r2search" and appends the hits (d2 + who) to a per-warp ring of 64
 // 16-byte entries in shared memory, at warp-aggregated positions (one ballot per iteration).  Whenever 32 hits are
@@ -335,6 +362,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     uint16_t *s_key = reinterpret_cast<uint16_t *>(smem_raw + off);
     __shared__ FrameGeom s_geom;
     __shared__ PairTile s_tile;
+    __shared__ __align__(8) unsigned long long s_mbar;
 
     const int S = a.n_species;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = TILE_THREADS / 32;
@@ -348,6 +376,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
         for (int k = threadIdx.x; k < a.nkeys; k += blockDim.x) { s_cnthr[k] = a.cn_thr2[k]; s_cn[k] = 0u; }
     for (int k = threadIdx.x; k < S * S; k += blockDim.x) s_key[k] = a.keyidx[k];
 
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+    if (TILE_TMA && threadIdx.x == 0) mbar_init(mbar, 1);
+    unsigned tma_phase = 0;
     const int n_tiles = min(*ta.n_tiles, ta.max_tiles);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();     // previous tile fully consumed (atoms, offsets, cn counters)
@@ -404,6 +435,40 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
             if (lane == 0) s_off[0] = 0;
         }
         __syncthreads();
+#if TILE_TMA
+        // One warp issues the copies: lane = task (row), each contiguous run of a row is ONE cp.async.bulk whose bytes
+        // complete on the block's mbarrier; everybody then waits on the barrier phase instead of moving the atoms
+        // through registers (3 200 load/store pairs per tile otherwise).
+        if (warp == 0) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the buffer are done
+                mbar_arrive_expect_tx(mbar, (unsigned)s_off[EH] * (unsigned)sizeof(SAtom));
+            }
+            __syncwarp();
+            const unsigned abase = (unsigned)__cvta_generic_to_shared(s_atoms);
+            for (int task = lane; task < RR + 1; task += 32) {
+                int colbase, va, vb, ebase;
+                if (task < RR) {
+                    int d0, d1, s0_, s1_, q0, q1;
+                    tile_row_offset(s_geom, rb + task, d0, d1);
+                    wrap_cell(c0 + d0, nc0, s0_, q0);
+                    wrap_cell(c1 + d1, nc1, s1_, q1);
+                    colbase = (q0 * nc1 + q1) * nc2; va = z0 - m2; vb = z0 + zlen + m2; ebase = task * V;
+                } else { colbase = homebase; va = z0; vb = z0 + zlen; ebase = E; }
+                int v = va;
+                while (v < vb) {                          // one contiguous run per wrap of the column
+                    int sdum, q;
+                    wrap_cell(v, nc2, sdum, q);
+                    const int run = min(vb - v, nc2 - q);
+                    const int src = (int)cs[colbase + q], n = (int)cs[colbase + q + run] - src;
+                    if (n > 0) bulk_g2s(abase + (unsigned)s_off[ebase + (v - va)] * (unsigned)sizeof(SAtom), fr + src, (unsigned)n * (unsigned)sizeof(SAtom), mbar);
+                    v += run;
+                }
+            }
+        }
+        mbar_wait(mbar, tma_phase);
+        tma_phase ^= 1u;
+#else
         for (int task = warp; task < RR + 1; task += nwarp) {
             // task < RR: row rb+task, virtual cells [z0-m2, z0+zlen+m2); task == RR: the home cells [z0, z0+zlen)
             int colbase, va, vb, ebase;
@@ -427,6 +492,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
             }
         }
         __syncthreads();
+#endif
 
 #if TILE_FLAT && !TILE_QUEUE
         // ---- compute: work item = (home cell, group of RG staged rows), scanned as one flat candidate list ----
