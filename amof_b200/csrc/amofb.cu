@@ -683,7 +683,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 PlanArgs pl;
                 pl.geom = s->d_geom; pl.cell_start = s->d_cell_start; pl.tiles = p->d_tiles; pl.n_tiles = p->d_ntiles;
                 pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles;
-                k_pair_plan<<<(unsigned)((columns + 127) / 128), 128, 0, ctx->s_compute>>>(pl);
+                k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(pl);      // one warp per column
                 TiledArgs ta;
                 ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;
                 ta.p.hard_mask = nullptr; ta.p.n_hard = nullptr;

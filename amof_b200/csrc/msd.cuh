@@ -216,8 +216,12 @@ __global__ void __launch_bounds__(256) k_msd_sum_groups(const double *__restrict
 // keeps R_k in registers and walks the window lengths, so each pair costs one shared-memory read of R_{k-m}.
 // The per-window sums stay in registers (MSD_NW per pass) across all atoms of one species; they are reduced over the
 // block only when the species changes, in a fixed order, so the result does not depend on scheduling.
+#ifndef MSD_NW
 #define MSD_NW 32
+#endif
+#ifndef MSD_THREADS
 #define MSD_THREADS 512
+#endif
 
 template <bool SMEM>
 __global__ void __launch_bounds__(MSD_THREADS) k_msd_window(const double *__restrict__ P, const uint8_t *__restrict__ species, int n, int T,

@@ -70,8 +70,9 @@ __device__ __forceinline__ int column_count(const uint32_t *cs, int colbase, int
 }
 
 __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
-    // thread -> (frame, column)
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // warp -> (frame, column); the lanes share the stencil rows when a tile's population is summed
+    const int lane = threadIdx.x & 31;
+    long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int f = 0;
     // frames may have different grids: walk the frames (n_frames is small next to the thread count)
     for (; f < a.n_frames; ++f) {
@@ -94,19 +95,21 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
         int total = 0;
         for (;;) {
             total = 0;
-            for (int r = 0; r < R; ++r) {
+            for (int r = lane; r < R; r += 32) {
                 int d0, d1;
                 tile_row_offset(g, r, d0, d1);
                 const int t0 = c0 + d0, t1 = c1 + d1;
                 const int q0 = t0 - floordiv_i(t0, g.nc[0]) * g.nc[0], q1 = t1 - floordiv_i(t1, nc1) * nc1;
                 total += column_count(cs, (q0 * nc1 + q1) * nc2, nc2, z - m2, z + zlen - 1 + m2);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             total += (int)(cs[homebase + z + zlen] - cs[homebase + z]);   // the home cells are staged once more
             if (total <= a.cap || zlen == 1) break;
             --zlen;
         }
         const int home = (int)(cs[homebase + z + zlen] - cs[homebase + z]);
-        if (home > 0) {
+        if (home > 0 && lane == 0) {                // every lane holds the same total; lane 0 records the decision
             if (total <= a.cap) {
                 int k = atomicAdd(&a.n_tiles[0], 1);
                 if (k < a.max_tiles) a.tiles[k] = PairTile{f, c0, c1, z, zlen, 0, R, 0};
