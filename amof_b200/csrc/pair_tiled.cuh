@@ -188,6 +188,36 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
         "}\n" :: "r"(mbar), "r"(parity) : "memory");
 }
 
+// shared-memory loads through an explicit 32-bit shared address kept in a register: the compiler otherwise
+// re-derives the shared window base (S2R SR_CgaCtaId + LEA) inside the candidate loop
+__device__ __forceinline__ void lds_xyz(unsigned addr, double &x, double &y, double &z) {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+    asm("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(addr));
+}
+__device__ __forceinline__ int lds_species(unsigned addr) {
+    unsigned v;
+    asm("ld.shared.u8 %0, [%1+24];" : "=r"(v) : "r"(addr));
+    return (int)v;
+}
+__device__ __forceinline__ int lds_u16(unsigned addr) {
+    unsigned short v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (int)v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void reds_inc(unsigned addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
+}
+// rdf_bin (pair.cuh) on a shared-memory threshold table given by its 32-bit shared address; margin > 0 path only
+__device__ __forceinline__ int rdf_bin_s(double d2, unsigned edge_addr, float inv_dr_f, float margin) {
+    const int b = (int)fmaf(sqrt_approx((float)d2), inv_dr_f, -margin);
+    return b + (d2 >= lds_f64(edge_addr + (unsigned)(b + 1) * 8u) ? 1 : 0);
+}
+
 // ---- hit queue -------------------------------------------------------------------------------------------
 // The candidate loop only decides "d2 < r2search" and appends the hits (d2 + who) to a per-warp ring of 64
 // 16-byte entries in shared memory, at warp-aggregated positions (one ballot per iteration).  Whenever 32 hits are
@@ -257,35 +287,31 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
     const float inv_dr_f = a.inv_dr_f, margin = a.bin_margin;
     const int nbins = a.nbins;
     const uint16_t *krow = s_key + (int)(me.s & 0xff) * a.n_species;
+    const unsigned abase = (unsigned)__cvta_generic_to_shared(s_atoms);     // one register instead of re-deriving the window base
+    const unsigned edge_addr = (unsigned)__cvta_generic_to_shared(s_edge2);
+    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(s_hist);
+    const unsigned krow_addr = (unsigned)__cvta_generic_to_shared(krow);
+    const unsigned cnthr_addr = HAS_CN ? (unsigned)__cvta_generic_to_shared(s_cnthr) : 0u;
+    const unsigned cn_addr = HAS_CN ? (unsigned)__cvta_generic_to_shared(s_cn) : 0u;
+    const unsigned astep = (unsigned)G * 32u;
+    unsigned addr = abase + (unsigned)(jb + sub) * 32u;
     TILE_PRAGMA_UNROLL(TILE_UNROLL)
-    for (int j = jb + sub; j < je; j += G) {
-        const double2 *q = reinterpret_cast<const double2 *>(s_atoms + j);
-        const double2 o0 = q[0], o1 = q[1];
-        double dx = o0.x - me.x, dy = o0.y - me.y, dz = o1.x - me.z;
+    for (int j = jb + sub; j < je; j += G, addr += astep) {
+        double ox, oy, oz;
+        lds_xyz(addr, ox, oy, oz);
+        double dx = ox - me.x, dy = oy - me.y, dz = oz - me.z;
         if (SHIFT) { dx += Tx; dy += Ty; dz += Tz; }
         const double dd = (dx * dx + dy * dy) + dz * dz;
         if (dd < r2search && !(AFTER && j <= ism)) {
-            const int key = krow[(int)(__double_as_longlong(o1.y) & 0xff)];
-            if (dd < r2max) {
-                const int b = rdf_bin(dd, s_edge2, inv_dr_f, margin, nbins);
-                atomicAdd(&s_hist[key * nbins + b], 1u);
+            const int key = lds_u16(krow_addr + 2u * (unsigned)lds_species(addr));
+            if (!HAS_CN || dd < r2max) {          // without cutoffs r2search == r2max
+                const int b = margin > 0.f ? rdf_bin_s(dd, edge_addr, inv_dr_f, margin) : rdf_bin(dd, s_edge2, inv_dr_f, margin, nbins);
+                reds_inc(hist_addr + 4u * (unsigned)(key * nbins + b));
             }
-            if (HAS_CN && dd < cn_r2max && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
+            if (HAS_CN && dd < cn_r2max && dd < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
         }
     }
 #endif
-}
-
-// shared-memory loads through an explicit 32-bit shared address kept in a register: the compiler otherwise
-// re-derives the shared window base (S2R SR_CgaCtaId + LEA) inside the candidate loop
-__device__ __forceinline__ void lds_xyz(unsigned addr, double &x, double &y, double &z) {
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
-    asm("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(addr));
-}
-__device__ __forceinline__ int lds_species(unsigned addr) {
-    unsigned v;
-    asm("ld.shared.u8 %0, [%1+24];" : "=r"(v) : "r"(addr));
-    return (int)v;
 }
 
 // ---- flat scan -------------------------------------------------------------------------------------------
@@ -469,8 +495,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
                 }
             }
         }
-        mbar_wait(mbar, tma_phase);
+        if (threadIdx.x == 0) mbar_wait(mbar, tma_phase);     // one poller; 511 spinning threads would eat issue slots
         tma_phase ^= 1u;
+        __syncthreads();
 #else
         for (int task = warp; task < RR + 1; task += nwarp) {
             // task < RR: row rb+task, virtual cells [z0-m2, z0+zlen+m2); task == RR: the home cells [z0, z0+zlen)
