@@ -161,6 +161,14 @@ struct TiledArgs {
     int max_tiles;
 };
 
+// G = 32 / ng sub-lanes per home atom and the magic multiplier of x / G (exact for x < 2048), by table: two integer
+// divisions per work item cost ~50 instructions on the SM
+__constant__ unsigned char c_sub_lanes[33] = {32, 32, 16, 10, 8, 6, 5, 4, 4, 3, 3, 2, 2, 2, 2, 2, 2,
+                                               1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+__constant__ unsigned short c_div_magic[33] = {0, 65535, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462,
+                                                5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622,
+                                                2521, 2428, 2341, 2260, 2185, 2115, 2048};
+
 // ---- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier ----------------------------------------
 #ifndef TILE_TMA
 #define TILE_TMA 1
@@ -618,8 +626,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
             const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // position of the home cell inside row 0
             for (int h0 = 0; h0 < nh; h0 += 32) {
                 const int ng = min(32, nh - h0);                 // home atoms in this group
-                const int G = 32 / ng;
-                const unsigned g_magic = (65536u + (unsigned)G - 1u) / (unsigned)G;
+                const int G = c_sub_lanes[ng];
+                const unsigned g_magic = G == 1 ? 65536u : c_div_magic[G];
                 const int il = (int)(((unsigned)lane * g_magic) >> 16), sub = lane - il * G;
                 const bool active = il < ng;
                 const int hidx = hb + h0 + (active ? il : 0);
