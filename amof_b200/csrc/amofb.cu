@@ -561,12 +561,12 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if ((rc = dev_alloc(ctx, &p->d_hist, hist_n))) return fail(rc);
     if (hist_n) cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * hist_n);
     // tiled kernel: shared memory = fixed tables + as many staged atoms as still let two blocks share an SM
-    if (p->smem_hist && n_atoms > 0 && !env_int("AMOFB_PAIR_GENERIC", 0)) {
+    if (p->smem_hist && n_atoms > 0 && p->bin_margin > 0.f && !env_int("AMOFB_PAIR_GENERIC", 0)) {
         size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + (TILE_QUEUE ? sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) : 0) +
                        sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32) + 64;
         int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", 2);
         size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
-        size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 512;
+        size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 2048;     // driver reserve + the kernel's static shared memory
         if (per_block > budget) per_block = budget;
         long long cap = per_block > fixed ? (long long)((per_block - fixed) / sizeof(SAtom)) : 0;
         int cap_env = env_int("AMOFB_TILE_CAP", 0);
@@ -595,7 +595,7 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
             } else cudaGetLastError();
         }
     }
-    if (p->smem_hist && n_atoms > 0 && env_int("AMOFB_PAIR_WARP", 0)) {
+    if (p->smem_hist && n_atoms > 0 && p->bin_margin > 0.f && env_int("AMOFB_PAIR_WARP", 0)) {
         p->warp_smem = smem_full + sizeof(SAtom) * 2 * WCHUNK * (WARP_THREADS / 32) + sizeof(uint32_t) * p->nkeys * (WARP_THREADS / 32) + 64;
         int per_sm = 0;
         cudaError_t e1 = p->has_cn
@@ -657,7 +657,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
             for (int f = 0; f < nf && tiled; ++f) {
                 const FrameGeom &g = s->h_geom[f];
                 int R = (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1);
-                if (R > TILE_MAX_ENTRIES || TILE_MAX_ENTRIES / R < 2 * g.m[2] + 1) tiled = false;
+                if (R > TILE_MAX_ROWS || TILE_MAX_ENTRIES / R < 2 * g.m[2] + 1) tiled = false;
                 ncell_total += (size_t)g.ncell + 1;
                 columns += (long long)g.nc[0] * g.nc[1];
             }

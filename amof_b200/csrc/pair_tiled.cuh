@@ -32,6 +32,7 @@
 #define TILE_PRAGMA_UNROLL(n) TILE_PRAGMA_(unroll n)
 #define TILE_MAX_ENTRIES 1024     // rows x virtual cells per tile
 #define TILE_MAX_ZLEN 62
+#define TILE_MAX_ROWS 256
 #define TILE_OFF_WORDS (TILE_MAX_ENTRIES + TILE_MAX_ZLEN + 2)   // offsets: entries + home cells + 1
 
 struct PairTile {
@@ -302,18 +303,20 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
     const unsigned cnthr_addr = HAS_CN ? (unsigned)__cvta_generic_to_shared(s_cnthr) : 0u;
     const unsigned cn_addr = HAS_CN ? (unsigned)__cvta_generic_to_shared(s_cn) : 0u;
     const unsigned astep = (unsigned)G * 32u;
-    unsigned addr = abase + (unsigned)(jb + sub) * 32u;
+    const unsigned aend = abase + (unsigned)je * 32u;
+    // AFTER: partners staged at or before me do not count (ism < 0: I am staged before this whole run -> nothing to skip)
+    const unsigned askip = ism >= 0 ? abase + (unsigned)ism * 32u : 0u;
     TILE_PRAGMA_UNROLL(TILE_UNROLL)
-    for (int j = jb + sub; j < je; j += G, addr += astep) {
+    for (unsigned addr = abase + (unsigned)(jb + sub) * 32u; addr < aend; addr += astep) {
         double ox, oy, oz;
         lds_xyz(addr, ox, oy, oz);
         double dx = ox - me.x, dy = oy - me.y, dz = oz - me.z;
         if (SHIFT) { dx += Tx; dy += Ty; dz += Tz; }
         const double dd = (dx * dx + dy * dy) + dz * dz;
-        if (dd < r2search && !(AFTER && j <= ism)) {
+        if (dd < r2search && !(AFTER && addr <= askip)) {
             const int key = lds_u16(krow_addr + 2u * (unsigned)lds_species(addr));
             if (!HAS_CN || dd < r2max) {          // without cutoffs r2search == r2max
-                const int b = margin > 0.f ? rdf_bin_s(dd, edge_addr, inv_dr_f, margin) : rdf_bin(dd, s_edge2, inv_dr_f, margin, nbins);
+                const int b = rdf_bin_s(dd, edge_addr, inv_dr_f, margin);      // the host only selects this kernel when margin > 0
                 reds_inc(hist_addr + 4u * (unsigned)(key * nbins + b));
             }
             if (HAS_CN && dd < cn_r2max && dd < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     __shared__ FrameGeom s_geom;
     __shared__ PairTile s_tile;
     __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ int s_rowimg[TILE_MAX_ROWS];        // per staged row: image (s0 | s1 << 16) of its column
 
     const int S = a.n_species;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = TILE_THREADS / 32;
@@ -441,6 +445,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
         // the column wraps, so a row is a few long coalesced runs.
         const int EH = E + zlen;                    // + home entries
         const int homebase = (c0 * nc1 + c1) * nc2;
+        for (int t = threadIdx.x; t < RR; t += blockDim.x) {
+            int d0, d1, s0_, s1_, q0_, q1_;
+            tile_row_offset(s_geom, rb + t, d0, d1);
+            wrap_cell(c0 + d0, nc0, s0_, q0_);
+            wrap_cell(c1 + d1, nc1, s1_, q1_);
+            s_rowimg[t] = (s0_ & 0xffff) | (s1_ << 16);
+        }
         for (int e = threadIdx.x; e < EH; e += blockDim.x) {
             int cell;
             if (e < E) {
@@ -613,14 +624,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
         const int items = zlen * RR;
         const unsigned rr_magic = (65536u + (unsigned)RR - 1u) / (unsigned)RR;    // exact x / RR for x < 2048
         for (int item = warp; item < items; item += nwarp) {     // (dynamic hand-out via an smem counter measured no better)
-            const int hz = (int)(((unsigned)item * rr_magic) >> 16), rr = item - hz * RR, r = rb + rr;            const int z = z0 + hz;
+            const int hz = (int)(((unsigned)item * rr_magic) >> 16), rr = item - hz * RR, r = rb + rr;
+            const int z = z0 + hz;
             const int hb = s_off[E + hz], nh = s_off[E + hz + 1] - hb;      // staged home cell
             if (nh == 0) continue;
-            int d0, d1;
-            tile_row_offset(s_geom, r, d0, d1);
-            int s0, s1, q0_, q1_;
-            wrap_cell(c0 + d0, nc0, s0, q0_);
-            wrap_cell(c1 + d1, nc1, s1, q1_);
+            const int img01 = s_rowimg[rr];                               // image of the row's column, prepared per tile
+            const int s0 = (int)(short)(img01 & 0xffff), s1 = img01 >> 16;
             const double fs0 = (double)s0, fs1 = (double)s1;
             const bool home_row = (r == 0);
             const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // position of the home cell inside row 0
