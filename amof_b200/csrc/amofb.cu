@@ -432,7 +432,7 @@ struct PairState {
     float inv_dr_f = 0.f, bin_margin = 0.f;
     double cn_r2max = 0.0;
     // tiled path (pair_tiled.cuh)
-    bool tiled = false;
+    bool tiled = false, cn_wide = false;
     PairTile *d_tiles = nullptr;
     int *d_ntiles = nullptr, *d_flags = nullptr;
     uint8_t *d_hard = nullptr;
@@ -576,12 +576,11 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
             p->tile_cap = (int)cap;
             p->tile_smem = fixed + sizeof(SAtom) * (size_t)cap;
             int per_sm = 0;
-            cudaError_t e1 = p->has_cn
-                ? cudaFuncSetAttribute(k_pair_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem)
-                : cudaFuncSetAttribute(k_pair_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-            if (e1 == cudaSuccess)
-                e1 = p->has_cn ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_tiled<true>, TILE_THREADS, p->tile_smem)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_tiled<false>, TILE_THREADS, p->tile_smem);
+            p->cn_wide = p->has_cn && p->cn_r2max > p->r2max;
+            const void *kfn = !p->has_cn ? (const void *)k_pair_tiled<false, false>
+                              : p->cn_wide ? (const void *)k_pair_tiled<true, true> : (const void *)k_pair_tiled<true, false>;
+            cudaError_t e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+            if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, TILE_THREADS, p->tile_smem);
             if (e1 == cudaSuccess && per_sm >= 1) {
                 p->tiled = true;
                 p->tile_grid = ctx->num_sms * per_sm;
@@ -687,8 +686,9 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 TiledArgs ta;
                 ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;
                 ta.p.hard_mask = nullptr; ta.p.n_hard = nullptr;
-                if (p->has_cn) k_pair_tiled<true><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
-                else k_pair_tiled<false><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
+                if (!p->has_cn) k_pair_tiled<false, false><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
+                else if (p->cn_wide) k_pair_tiled<true, true><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
+                else k_pair_tiled<true, false><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
                 ctx->launches += 2;
                 CUDA_TRY(ctx, cudaGetLastError());
                 a.hard_mask = p->d_hard;          // clean-up launch: only the home cells the plan could not tile

@@ -262,7 +262,8 @@ __device__ __forceinline__ void hits_flush(const PairArgs &a, const SAtom *__res
 // One run of staged candidates [jb, je) against the home atoms of this warp: lane (il, sub) takes jb+sub, +G, ...
 //   SHIFT: the run sits in a periodic image (T != 0); without it (pj - pi) + 0 == pj - pi bit for bit, so the adds go.
 //   AFTER: the run starts with the home cell itself: only partners staged after me (index > ism) count.
-template <bool HAS_CN, bool SHIFT, bool AFTER>
+// CN_WIDE: some cutoff exceeds rmax, so a candidate inside r2search can still be outside the RDF range
+template <bool HAS_CN, bool CN_WIDE, bool SHIFT, bool AFTER>
 __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restrict__ s_atoms, const double *__restrict__ s_edge2,
                                          const double *__restrict__ s_cnthr, uint32_t *__restrict__ s_hist, uint32_t *__restrict__ s_cn,
                                          const uint16_t *__restrict__ s_key, HitQueue &hq, const SAtom &me, double Tx, double Ty, double Tz,
@@ -315,7 +316,7 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
         const double dd = (dx * dx + dy * dy) + dz * dz;
         if (dd < r2search && !(AFTER && addr <= askip)) {
             const int key = lds_u16(krow_addr + 2u * (unsigned)lds_species(addr));
-            if (!HAS_CN || dd < r2max) {          // without cutoffs r2search == r2max
+            if (!CN_WIDE || dd < r2max) {         // r2search == r2max unless a cutoff reaches beyond rmax
                 const int b = rdf_bin_s(dd, edge_addr, inv_dr_f, margin);      // the host only selects this kernel when margin > 0
                 reds_inc(hist_addr + 4u * (unsigned)(key * nbins + b));
             }
@@ -382,7 +383,7 @@ __device__ __forceinline__ void scan_flat(const PairArgs &a, const SAtom *__rest
     }
 }
 
-template <bool HAS_CN>
+template <bool HAS_CN, bool CN_WIDE>
 __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(TiledArgs ta) {
     const PairArgs &a = ta.p;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -656,11 +657,11 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
                         const double Tx = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
                         const double Ty = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
                         const double Tz = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
-                        if (after_me) scan_run<HAS_CN, true, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
-                        else scan_run<HAS_CN, true, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        if (after_me) scan_run<HAS_CN, CN_WIDE, true, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        else scan_run<HAS_CN, CN_WIDE, true, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
                     } else {
-                        if (after_me) scan_run<HAS_CN, false, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
-                        else scan_run<HAS_CN, false, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        if (after_me) scan_run<HAS_CN, CN_WIDE, false, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        else scan_run<HAS_CN, CN_WIDE, false, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
                     }
                     d2 += len;
                 }

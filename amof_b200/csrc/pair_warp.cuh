@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(WARP_THREADS, 2) k_pair_warp(WarpArgs wa) {
                     const double Tx = (fs0 * G.cell[0] + fs1 * G.cell[3]) + fs2 * G.cell[6];
                     const double Ty = (fs0 * G.cell[1] + fs1 * G.cell[4]) + fs2 * G.cell[7];
                     const double Tz = (fs0 * G.cell[2] + fs1 * G.cell[5]) + fs2 * G.cell[8];
-                    if (c_after) scan_run<HAS_CN, true, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
-                    else scan_run<HAS_CN, true, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
+                    if (c_after) scan_run<HAS_CN, true, true, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
+                    else scan_run<HAS_CN, true, true, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
                 } else {
-                    if (c_after) scan_run<HAS_CN, false, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
-                    else scan_run<HAS_CN, false, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
+                    if (c_after) scan_run<HAS_CN, true, false, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
+                    else scan_run<HAS_CN, true, false, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
                 }
                 __syncwarp();
                 cur ^= 1;
