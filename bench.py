@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 
 CN_SETS = {'Zn-N': 2.5, 'C-N': 1.728, 'C-C': 1.752}
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_pair_tiled launch (107 frames of C2), ncu --set full,
-# profiles/r01_k_pair_tiled_ncu_full_summary.txt: 56.59 MB + 2.10 MB (the kernel reads the 32-byte cell-sorted records)
-PAIR_TRAFFIC = {"c2": 58.69e6}
+# profiles/r01_k_pair_tiled_ncu_full_summary.txt: 56.23 MB + 0.98 MB (the kernel reads the 32-byte cell-sorted records)
+PAIR_TRAFFIC = {"c2": 57.21e6}
 FP64_NOFMA_GOPS = 18515.3      # measured on this pool's B200 with tools/microbench.cu (gpurun_out/microbench.json)
 
 
