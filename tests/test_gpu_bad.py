@@ -85,3 +85,30 @@ def test_cutoff_precondition(backend):
     cut = np.full((2, 2), 4.5)      # above half the cell height (cell edges are 6.0 .. 7.8)
     with pytest.raises(ValueError):
         backend.bad_counts(spec, 2, [(pos[None], cell[None])], cut, [(0, 1)], 0.05, 3600)
+
+
+def test_too_many_neighbours_is_an_error(backend):
+    """more than 32 B-neighbours around a centre is refused (AMOFB_BAD_MAX_CN), like the oracle"""
+    rng = np.random.default_rng(0)
+    cell = np.diag([30.0, 30.0, 30.0])
+    pos = np.vstack([[15.0, 15.0, 15.0], 15.0 + rng.normal(scale=0.8, size=(60, 3))])
+    spec = np.array([0] + [1] * 60, dtype=np.uint8)
+    cut = np.array([[0.0, 6.0], [6.0, 0.0]])
+    with pytest.raises(ValueError):
+        backend.bad_counts(spec, 2, [(pos[None], cell[None])], cut, [(0, 1)], 1.0, 181)
+    ok = backend.bad_counts(spec, 2, [(pos[None], cell[None])], np.array([[0.0, 0.5], [0.5, 0.0]]), [(0, 1)], 1.0, 181)
+    assert ok[2] == 1
+
+
+def test_many_frames_streaming(backend, monkeypatch):
+    monkeypatch.setenv("AMOFB_BATCH_ATOMS", "3000")
+    T, n = 23, 400
+    rng = np.random.default_rng(2)
+    base, cell0, spec = random_box(90, n, 2, True, 14.0)
+    pos = base[None] + rng.normal(scale=0.2, size=(T, n, 3))
+    cell = np.array([cell0 * (1 + 0.001 * f) for f in range(T)])
+    cut = np.array([[0.0, 2.7], [2.7, 2.2]])
+    triples = [(0, 1), (1, 1), (1, -1)]
+    hist, dropped, nf = backend.bad_counts(spec, 2, [(pos[:9], cell[:9]), (pos[9:], cell[9:])], cut, triples, 0.5, 361)
+    want, wdrop = _oracle(pos, cell, spec, 2, cut, triples, 0.5, 361)
+    assert nf == T and np.array_equal(hist, want) and np.array_equal(dropped, wdrop)

@@ -150,3 +150,34 @@ def test_kernel_variants_agree(backend, monkeypatch, env):
     res = backend.pair_counts(spec, S, [(pos[None], cell[None])], rmax=9.0, nbins=900, cn_cutoff=cut)
     assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell, spec, S, 9.0, 900))
     assert np.array_equal(res["cn"][0], orc.cn_counts(pos, cell, spec, S, cut))
+
+
+@pytest.mark.parametrize("S,nbins", [(1, 500), (16, 300), (16, 999), (7, 2000)])
+def test_species_counts_and_histogram_placement(backend, S, nbins):
+    """1 species; 16 species (136 folded pairs: the histogram leaves shared memory for the global-atomic path at 999
+    bins, stays in shared memory at 300); 7 species with 2000 bins."""
+    pos, cell, spec = random_box(70 + S, 900, S, True, 17.0)
+    cut = np.zeros((S, S))
+    cut[0, S - 1] = cut[S - 1, 0] = 3.0
+    res = backend.pair_counts(spec, S, [(pos[None], cell[None])], rmax=8.0, nbins=nbins, cn_cutoff=cut)
+    assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell, spec, S, 8.0, nbins))
+    assert np.array_equal(res["cn"][0], orc.cn_counts(pos, cell, spec, S, cut))
+    with pytest.raises(ValueError):
+        backend.pair_counts(np.zeros(10, dtype=np.uint8), 17, [(pos[None, :10], cell[None])], rmax=4.0, nbins=10)
+
+
+def test_cutoffs_beyond_rmax(backend):
+    """coordination cutoffs larger than rmax (the CN_WIDE kernel variant): pairs counted for CN but not binned"""
+    pos, cell, spec = random_box(81, 1200, 3, True, 20.0)
+    cut = np.array([[6.5, 0.0, 5.0], [0.0, 0.0, 7.25], [5.0, 7.25, 3.0]])
+    res = backend.pair_counts(spec, 3, [(pos[None], cell[None])], rmax=4.0, nbins=400, cn_cutoff=cut)
+    assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell, spec, 3, 4.0, 400))
+    assert np.array_equal(res["cn"][0], orc.cn_counts(pos, cell, spec, 3, cut))
+
+
+def test_repeated_analyses_reuse_pooled_buffers(backend):
+    """begin/finish cycles of different shapes on one context (buffers come back from the pool, sizes differ)"""
+    for n, S, nb in [(200, 2, 100), (1500, 4, 999), (50, 1, 10), (1500, 4, 999), (700, 3, 50)]:
+        pos, cell, spec = random_box(n, n, S, True, 14.0)
+        res = backend.pair_counts(spec, S, [(pos[None], cell[None])], rmax=6.0, nbins=nb)
+        assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell, spec, S, 6.0, nb))
