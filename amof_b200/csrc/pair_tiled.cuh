@@ -402,7 +402,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     FlatRun *s_runs = reinterpret_cast<FlatRun *>(smem_raw + off);         off += sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32);
     uint16_t *s_key = reinterpret_cast<uint16_t *>(smem_raw + off);
     __shared__ FrameGeom s_geom;
-    __shared__ PairTile s_tile;
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_rowimg[TILE_MAX_ROWS];        // per staged row: image (s0 | s1 << 16) of its column
 
@@ -423,9 +422,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     unsigned tma_phase = 0;
     const int n_tiles = min(*ta.n_tiles, ta.max_tiles);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();     // previous tile fully consumed (atoms, offsets, cn counters)
-        if (threadIdx.x < 8) reinterpret_cast<int *>(&s_tile)[threadIdx.x] = reinterpret_cast<const int *>(&ta.tiles[tile])[threadIdx.x];
-        __syncthreads();
+        __syncthreads();     // previous tile fully consumed (atoms, offsets, geometry, cn counters)
+        // every thread reads the 32-byte tile record itself (one broadcast line from L2): no shared copy, no barrier
+        const int4 t_lo = __ldg(reinterpret_cast<const int4 *>(&ta.tiles[tile]));
+        const int4 t_hi = __ldg(reinterpret_cast<const int4 *>(&ta.tiles[tile]) + 1);
+        PairTile s_tile;
+        s_tile.frame = t_lo.x; s_tile.c0 = t_lo.y; s_tile.c1 = t_lo.z; s_tile.z0 = t_lo.w;
+        s_tile.zlen = t_hi.x; s_tile.rb = t_hi.y; s_tile.re = t_hi.z; s_tile.pad = 0;
         const int f = s_tile.frame;
         if (threadIdx.x < (int)(sizeof(FrameGeom) / sizeof(int)))
             reinterpret_cast<int *>(&s_geom)[threadIdx.x] = reinterpret_cast<const int *>(&a.geom[f])[threadIdx.x];
