@@ -266,6 +266,25 @@ def test_extxyz_reader_roundtrip(tmp_path, zif4):
     assert np.array_equal(fr[0].cell, zif4.cell)
 
 
+def test_fast_extxyz_trajectory_reader(tmp_path):
+    traj = small_traj(4)
+    p = tmp_path / "t.xyz"
+    with open(p, "w") as fh:
+        for a in traj:
+            lat = " ".join(repr(float(x)) for x in a.cell.ravel())
+            fh.write("%d\n" % len(a))
+            fh.write('Lattice="%s" Properties=species:S:1:pos:R:3:occ:R:1 pbc="T T T"\n' % lat)
+            for s, r in zip(a.get_chemical_symbols(), a.positions):
+                fh.write("%-2s %r %r %r 1.0\n" % (s, float(r[0]), float(r[1]), float(r[2])))
+    arr = amof_b200.trajectory.read_extxyz_trajectory(p)
+    assert len(arr) == 4 and np.array_equal(arr.numbers, traj[0].numbers)
+    assert np.array_equal(arr.positions, np.array([a.positions for a in traj]))
+    assert np.array_equal(arr.cells, np.array([a.cell for a in traj]))
+    slow = amof_b200.read_extxyz(p)
+    assert np.array_equal(slow[3].positions, arr.positions[3])
+    assert_frames_equal(amof_b200.rdf.Rdf.from_trajectory(arr, dr=0.05).data, amof_b200.rdf.Rdf.from_trajectory(traj, dr=0.05).data, rtol=0)
+
+
 def test_synthetic_configs_are_deterministic():
     a = synth.make_trajectory("c2", 3)
     b = synth.make_trajectory("c2", 3)
