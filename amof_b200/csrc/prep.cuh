@@ -146,7 +146,18 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         // species | c0 << 8 | c1 << 20 | c2 << 32   (nc <= 1024 per axis)
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
-        if (a.species_flag && a.species_flag[a.species[i]])
-            a.centres[atomicAdd(a.n_centres, 1)] = (uint32_t)((long long)f * a.n_atoms + dst);
+        if (a.species_flag) {
+            // warp-aggregated append: one atomic per warp on the single list counter instead of one per centre
+            const bool is_centre = a.species_flag[a.species[i]] != 0;
+            const unsigned active = __activemask();
+            const unsigned m = __ballot_sync(active, is_centre);
+            if (m) {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(a.n_centres, __popc(m));
+                base = __shfl_sync(active, base, leader);
+                if (is_centre) a.centres[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)((long long)f * a.n_atoms + dst);
+            }
+        }
     }
 }
