@@ -28,6 +28,9 @@
 #ifndef TILE_QUEUE
 #define TILE_QUEUE 0
 #endif
+#ifndef TILE_PAIRED
+#define TILE_PAIRED 1
+#endif
 #define TILE_PRAGMA_(x) _Pragma(#x)
 #define TILE_PRAGMA_UNROLL(n) TILE_PRAGMA_(unroll n)
 #define TILE_MAX_ENTRIES 1024     // rows x virtual cells per tile
@@ -307,21 +310,41 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
     const unsigned aend = abase + (unsigned)je * 32u;
     // AFTER: partners staged at or before me do not count (ism < 0: I am staged before this whole run -> nothing to skip)
     const unsigned askip = ism >= 0 ? abase + (unsigned)ism * 32u : 0u;
+    // the hit work (exact bin + shared-memory increment), shared by the paired and the tail iteration
+    auto hit = [&](unsigned addr, double dd) {
+        const int key = lds_u16(krow_addr + 2u * (unsigned)lds_species(addr));
+        if (!CN_WIDE || dd < r2max) {             // r2search == r2max unless a cutoff reaches beyond rmax
+            const int b = rdf_bin_s(dd, edge_addr, inv_dr_f, margin);          // the host only selects this kernel when margin > 0
+            reds_inc(hist_addr + 4u * (unsigned)(key * nbins + b));
+        }
+        if (HAS_CN && dd < cn_r2max && dd < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
+    };
+    unsigned addr = abase + (unsigned)(jb + sub) * 32u;
+#if TILE_PAIRED
+    // two candidates per trip: both distance chains are in flight together (the fp64 chain is latency-bound at
+    // 8 warps per scheduler), and the loop overhead is paid once per pair
+    for (; addr + astep < aend; addr += 2u * astep) {
+        const unsigned addr1 = addr + astep;
+        double ox0, oy0, oz0, ox1, oy1, oz1;
+        lds_xyz(addr, ox0, oy0, oz0);
+        lds_xyz(addr1, ox1, oy1, oz1);
+        double dx0 = ox0 - me.x, dy0 = oy0 - me.y, dz0 = oz0 - me.z;
+        double dx1 = ox1 - me.x, dy1 = oy1 - me.y, dz1 = oz1 - me.z;
+        if (SHIFT) { dx0 += Tx; dy0 += Ty; dz0 += Tz; dx1 += Tx; dy1 += Ty; dz1 += Tz; }
+        const double dd0 = (dx0 * dx0 + dy0 * dy0) + dz0 * dz0;
+        const double dd1 = (dx1 * dx1 + dy1 * dy1) + dz1 * dz1;
+        if (dd0 < r2search && !(AFTER && addr <= askip)) hit(addr, dd0);
+        if (dd1 < r2search && !(AFTER && addr1 <= askip)) hit(addr1, dd1);
+    }
+#endif
     TILE_PRAGMA_UNROLL(TILE_UNROLL)
-    for (unsigned addr = abase + (unsigned)(jb + sub) * 32u; addr < aend; addr += astep) {
+    for (; addr < aend; addr += astep) {
         double ox, oy, oz;
         lds_xyz(addr, ox, oy, oz);
         double dx = ox - me.x, dy = oy - me.y, dz = oz - me.z;
         if (SHIFT) { dx += Tx; dy += Ty; dz += Tz; }
         const double dd = (dx * dx + dy * dy) + dz * dz;
-        if (dd < r2search && !(AFTER && addr <= askip)) {
-            const int key = lds_u16(krow_addr + 2u * (unsigned)lds_species(addr));
-            if (!CN_WIDE || dd < r2max) {         // r2search == r2max unless a cutoff reaches beyond rmax
-                const int b = rdf_bin_s(dd, edge_addr, inv_dr_f, margin);      // the host only selects this kernel when margin > 0
-                reds_inc(hist_addr + 4u * (unsigned)(key * nbins + b));
-            }
-            if (HAS_CN && dd < cn_r2max && dd < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
-        }
+        if (dd < r2search && !(AFTER && addr <= askip)) hit(addr, dd);
     }
 #endif
 }
