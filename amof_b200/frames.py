@@ -81,7 +81,7 @@ def check_same_atoms(trajectory, numbers, lo, hi):
                              "amof_b200 needs a fixed atom order over the trajectory" % k)
 
 
-def iter_chunks(trajectory, lo, hi, backend, target_bytes=64 << 20):
+def iter_chunks(trajectory, lo, hi, backend, target_bytes=192 << 20):
     """Yield (positions[F][N][3], cell[F][3][3]) for frames [lo, hi).
 
     ArrayTrajectory: zero-copy slices.  Otherwise frames are packed into two alternating page-locked buffers
