@@ -1,6 +1,6 @@
 // bad.cuh -- bond-angle triplet kernel (K4 of SURVEY.md 2.1).
 //
-// One thread owns one centre atom (from the compacted centre list) of the cell-sorted frame: it walks the FULL stencil, keeps the unit vectors of
+// One thread owns one centre atom (from the centre list k_cell_scatter compacts) of the cell-sorted frame: it walks the FULL stencil, keeps the unit vectors of
 // every neighbour under the pair cutoffs (P5), then for each requested (A, B) triple enumerates the unordered
 // pairs of its B-neighbours.  The angle itself is never formed on the device: x = u_p . u_q is computed in fp64
 // in the oracle's operation order (P6) and located in a table of thresholds on -x that the host bisected with its

@@ -3,16 +3,19 @@
 // The generic kernel of pair.cuh reads every candidate atom through L1/L2 once per home atom; at 10 A the candidate
 // set of a 256-atom tile (~200 KB) does not fit in L1, so it runs at L2 speed.  Here a block owns a HOME TILE = a run
 // of `zlen` consecutive cells of one column along the fastest cell axis, and first copies the tile's whole half
-// stencil -- R rows (neighbour columns) x (zlen + 2*m2) virtual cells -- into shared memory, cell by cell, so that
-// each row is one contiguous run ordered by virtual cell.  Every candidate is then read from shared memory.
+// stencil -- R rows (neighbour columns) x (zlen + 2*m2) virtual cells -- into shared memory with TMA 1-D bulk copies
+// (one cp.async.bulk per contiguous run of a row, completing on an mbarrier), so that each row is one contiguous run
+// ordered by virtual cell.  Every candidate is then read from shared memory.
 //
-//   k_pair_plan   one thread per column: greedy split of the column into tiles whose staged atoms fit `cap`;
+//   k_pair_plan   one warp per column: greedy split of the column into tiles whose staged atoms fit `cap`;
 //                 cells too dense even alone are split by rows, or marked "hard" and left to the generic kernel.
 //   k_pair_tiled  persistent blocks over the tile list.  Work item = (home cell, row); a warp takes one item:
 //                 lanes = (home atom i, sub-lane s) with G = 32 / n_home sub-lanes per home atom striding the
 //                 candidate run, so control flow is warp-uniform and shared-memory reads are G-way contiguous.
 //
 // Arithmetic, thresholds, folding of species pairs and histogram privatisation are exactly those of pair.cuh.
+// Compile-time switches kept for the measurements in DESIGN.md section 8: TILE_QUEUE (warp-aggregated hit queue),
+// TILE_FLAT (one flat scan per item), TILE_PAIRED (two candidates per trip), TILE_TMA (bulk-copy staging).
 #pragma once
 #include "pair.cuh"
 

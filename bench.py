@@ -422,7 +422,7 @@ def run_ours(args):
         ach = wl.algorithmic_bytes_per_frame() * frames_per_launch / (per_launch_ms / 1e3) / 1e9
         pairs = u["pair_evals_per_step"] * args.steps
         fp64 = 10.0 * pairs / (k_ms / 1e3) / 1e9
-        out["roofline"] = {"bound": "hbm", "kernel": "k_pair", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        out["roofline"] = {"bound": "hbm", "kernel": "k_pair_tiled (+ k_pair_plan)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                            "traffic": PAIR_TRAFFIC.get(wl.name), "peak_source": how, "kernel_ms_per_launch": per_launch_ms, "launches": int(k_n),
                            "algorithmic_bytes_per_launch": wl.algorithmic_bytes_per_frame() * frames_per_launch,
                            "kernel_share_of_step": k_ms / dev_ms,
