@@ -9,16 +9,44 @@ two alternating pinned buffers: while the GPU works on chunk k the interpreter p
 :class:`ArrayTrajectory` is an array-backed trajectory (still a valid aMOF trajectory: indexing yields Atoms)
 whose chunks are handed to the GPU without any per-frame Python work.
 """
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from . import _dist
 from .atoms import Atoms
 
+_POOL = None
+_POOL_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))
+
+
+def _parallel_copy(dst, sources):
+    """dst[i] = sources[i] for every frame, split over a few threads: numpy releases the GIL inside large copies, and
+    one core's memcpy (~10 GB/s) is slower than the PCIe link the chunk is about to cross."""
+    global _POOL
+    n = len(sources)
+    if n == 0:
+        return
+    if _POOL_THREADS == 1 or n < 2 * _POOL_THREADS:
+        for i, src in enumerate(sources):
+            dst[i] = src
+        return
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=_POOL_THREADS)
+
+    def work(lo, hi):
+        for i in range(lo, hi):
+            dst[i] = sources[i]
+    cuts = [(n * t) // _POOL_THREADS for t in range(_POOL_THREADS + 1)]
+    list(_POOL.map(lambda ab: work(*ab), zip(cuts[:-1], cuts[1:])))
+
 
 class ArrayTrajectory:
     """A trajectory stored as arrays: ``numbers[N]``, ``positions[T][N][3]``, ``cells[T][3][3]`` (or one [3][3])."""
 
-    def __init__(self, numbers, positions, cells, masses=None):
+    def __init__(self, numbers, positions, cells, masses=None, pinned=False):
+        self.pinned = bool(pinned)       # positions live in page-locked memory (Context.pinned_empty): copied as they are
         self.numbers = np.asarray(numbers, dtype=np.int64)
         self.positions = np.asarray(positions, dtype=np.float64)
         if self.positions.ndim != 3 or self.positions.shape[1:] != (len(self.numbers), 3):
@@ -34,7 +62,7 @@ class ArrayTrajectory:
 
     def __getitem__(self, k):
         if isinstance(k, slice):
-            return ArrayTrajectory(self.numbers, self.positions[k], self.cells[k], self.masses)
+            return ArrayTrajectory(self.numbers, self.positions[k], self.cells[k], self.masses, self.pinned)
         a = Atoms(numbers=self.numbers, positions=self.positions[k], cell=self.cells[k], masses=self.masses)
         a._parent = (self, k)
         return a
@@ -70,34 +98,52 @@ def frame_range(n_frames, distributed=None):
     return lo, hi
 
 
+def _numbers_of(atoms):
+    z = getattr(atoms, "numbers", None)          # ase.Atoms.numbers / our shim: the array itself, no copy
+    return atoms.get_atomic_numbers() if z is None else z
+
+
 def check_same_atoms(trajectory, numbers, lo, hi):
     """The C ABI takes one species vector per analysis; aMOF trajectories keep atom order fixed."""
     if isinstance(trajectory, ArrayTrajectory):
         return
     for k in range(lo, hi):
-        z = trajectory[k].get_atomic_numbers()
+        z = _numbers_of(trajectory[k])
+        if z is numbers:
+            continue
         if len(z) != len(numbers) or not np.array_equal(z, numbers):
             raise ValueError("frame %d has different atoms (count or order) than frame 0; "
                              "amof_b200 needs a fixed atom order over the trajectory" % k)
+
+
+def gather_cells(trajectory, lo=0, hi=None):
+    """cells[hi-lo][3][3] of the frames [lo, hi)"""
+    hi = len(trajectory) if hi is None else hi
+    if isinstance(trajectory, ArrayTrajectory):
+        return trajectory.cells[lo:hi]
+    out = np.empty((max(hi - lo, 0), 3, 3))
+    for k in range(lo, hi):
+        out[k - lo] = _cell_of(trajectory[k])
+    return out
 
 
 def iter_chunks(trajectory, lo, hi, backend, target_bytes=192 << 20):
     """Yield (positions[F][N][3], cell[F][3][3]) for frames [lo, hi).
 
     ArrayTrajectory: zero-copy slices.  Otherwise frames are packed into two alternating page-locked buffers
-    obtained from the backend's context (plain numpy buffers when the backend has none)."""
+    obtained from the backend's context (plain numpy buffers when the backend has none); the per-frame work in the
+    interpreter is two attribute reads, the copies of a chunk are one ``np.concatenate`` into the buffer."""
     if hi <= lo:
         return
-    if isinstance(trajectory, ArrayTrajectory):
-        n = max(len(trajectory.numbers), 1)
-        step = max(1, int(target_bytes // (24 * n)))
+    ctx = getattr(backend, "ctx", None)
+    is_array = isinstance(trajectory, ArrayTrajectory)
+    n = len(trajectory.numbers) if is_array else len(trajectory[lo])
+    step = max(1, min(hi - lo, int(target_bytes // (24 * max(n, 1)))))
+    if is_array and (trajectory.pinned or ctx is None):
         for a in range(lo, hi, step):
             b = min(hi, a + step)
             yield trajectory.positions[a:b], trajectory.cells[a:b]
         return
-    n = len(trajectory[lo])
-    step = max(1, min(hi - lo, int(target_bytes // (24 * max(n, 1)))))
-    ctx = getattr(backend, "ctx", None)
     if ctx is not None:
         bufs = [ctx.scratch("frames%d" % i, (step, n, 3)) for i in range(2)]
     else:
@@ -109,9 +155,14 @@ def iter_chunks(trajectory, lo, hi, backend, target_bytes=192 << 20):
         which ^= 1
         if ctx is not None:
             ctx.sync_copies()            # the copy that last read this buffer has finished
-        cells = np.empty((b - a, 3, 3))
-        for k in range(a, b):
-            fr = trajectory[k]
-            buf[k - a] = _positions_of(fr)
-            cells[k - a] = _cell_of(fr)
+        if is_array:                     # pageable array: stage it ourselves, threaded, instead of the driver's bounce
+            _parallel_copy(buf, [trajectory.positions[k] for k in range(a, b)])
+            cells = trajectory.cells[a:b]
+        else:
+            frames_ = [trajectory[k] for k in range(a, b)]
+            if n > 0:
+                _parallel_copy(buf, [_positions_of(fr) for fr in frames_])
+            cells = np.empty((b - a, 3, 3))
+            for i, fr in enumerate(frames_):
+                cells[i] = _cell_of(fr)
         yield buf[:b - a], cells

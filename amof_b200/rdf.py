@@ -31,10 +31,11 @@ logger = logging.getLogger(__name__)
 
 
 def _half_cell_rmax(trajectory):
-    """min over frames and axes of the cell LENGTHS / 2 (rdf.py:74; lengths, not perpendicular heights)."""
-    if isinstance(trajectory, frames.ArrayTrajectory):
-        return float(np.min(np.sqrt((trajectory.cells ** 2).sum(axis=2))) / 2)
-    return np.min([a for t in trajectory for a in t.get_cell_lengths_and_angles()[0:3]]) / 2
+    """min over frames and axes of the cell LENGTHS / 2 (rdf.py:74; lengths, not perpendicular heights).
+    One vectorised pass over the stacked cells instead of ``get_cell_lengths_and_angles()`` per frame (which also
+    evaluates three arccos per frame that the reference then discards)."""
+    cells = frames.gather_cells(trajectory)
+    return float(np.min(np.sqrt((cells ** 2).sum(axis=2))) / 2)
 
 
 def normalise_counts(counts, n_centres, n_frames, n_atoms, volume_mean, rmax):
@@ -53,7 +54,7 @@ def pair_histograms(trajectory, rmax, bins, cn_cutoff=None, distributed=None, ba
     Returns (zs, spec, result) with result = dict(hist, cn, n_frames, volume_sum) as in GpuBackend.pair_counts;
     ``hist`` is summed over ranks (integer all-reduce), ``cn`` rows are gathered in frame order."""
     backend = backend or _lib.get_backend()
-    numbers = np.asarray(trajectory[0].get_atomic_numbers())
+    numbers = np.asarray(frames._numbers_of(trajectory[0]))
     zs, spec = frames.species_index(numbers)
     T = len(trajectory)
     lo, hi = frames.frame_range(T, distributed)

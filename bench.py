@@ -146,7 +146,7 @@ class PairWorkload:
         self.n_atoms = len(numbers)
         self.host = ctx.pinned_empty((self.T, self.n_atoms, 3))
         synth.fill_frames(self.name, 0, self.T, self.host)
-        self.traj = ArrayTrajectory(numbers, self.host, cell)
+        self.traj = ArrayTrajectory(numbers, self.host, cell, pinned=True)
         self.zs, self.spec = fr.species_index(numbers)
         self.cut = amatom.cutoff_matrix(amatom.format_cutoff(CN_SETS), self.zs)
         self.bytes_in = self.host.nbytes + self.T * 72
@@ -214,7 +214,7 @@ class BadWorkload:
         self.n_atoms = len(numbers)
         self.host = ctx.pinned_empty((self.T, self.n_atoms, 3))
         synth.fill_frames(self.name, 0, self.T, self.host)
-        self.traj = ArrayTrajectory(numbers, self.host, cell)
+        self.traj = ArrayTrajectory(numbers, self.host, cell, pinned=True)
         self.zs, self.spec = fr.species_index(numbers)
         self.cut = amatom.cutoff_matrix(amatom.format_cutoff({'Zn-N': 2.5}), self.zs)
         self.triples = [(self.zs.index(30), self.zs.index(7)), (self.zs.index(7), self.zs.index(30))]
