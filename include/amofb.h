@@ -87,7 +87,8 @@ int amofb_memcpy_d2h(amofb_ctx *ctx, void *dst_host, const void *src_device, uin
  *         counted iff < nbins); cn_cutoff != NULL (double[n_species][n_species], symmetric, 0 = pair not
  *         listed) enables per-frame neighbour counts with the strict test d < cutoff[Zi][Zj].
  * push  : n_frames frames in host memory (pinned memory is copied asynchronously, pageable memory is
- *         staged).  push_device: positions already in device memory (cells still on the host).
+ *         staged).  push_device: positions already in device memory (cells still on the host); the data must be
+ *         complete when the call is made (the library reads it on its own stream) and stay valid until finish/sync.
  * finish: hist       uint64[n_species][n_species][nbins]  directed pair counts, summed over frames (or NULL)
  *         cn_counts  uint64[cn_frames][n_species][n_species] directed neighbour pairs per frame (or NULL);
  *                    cn_frames must equal the number of frames pushed
