@@ -510,10 +510,15 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     std::vector<double> edge2((size_t)nbins + 1, 0.0), cnthr((size_t)p->nkeys, 0.0);
     if (p->has_rdf) {
         const double dr = rmax / (double)nbins;
-        for (int b = 1; b <= nbins; ++b) {
-            const double fb = (double)b;
-            double guess = (fb * dr) * (fb * dr);
-            edge2[b] = host_threshold(guess, [&](double t) { return sqrt(t) / dr >= fb; });
+        if (ctx->edge_nbins == nbins && ctx->edge_rmax == rmax && (int)ctx->edge_cache.size() == nbins + 1) {
+            edge2 = ctx->edge_cache;                  // same axis as the previous analysis: reuse the bisected table
+        } else {
+            for (int b = 1; b <= nbins; ++b) {
+                const double fb = (double)b;
+                double guess = (fb * dr) * (fb * dr);
+                edge2[b] = host_threshold(guess, [&](double t) { return sqrt(t) / dr >= fb; });
+            }
+            ctx->edge_cache = edge2; ctx->edge_rmax = rmax; ctx->edge_nbins = nbins;
         }
         p->r2max = edge2[nbins];
         p->inv_dr_f = (float)((double)nbins / rmax);

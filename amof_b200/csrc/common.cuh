@@ -35,6 +35,10 @@ struct PoolBlock {
 
 struct amofb_ctx {
     int device = 0;
+    // last RDF threshold table (amof.rdf.CoordinationNumber opens one analysis per frame with the same rmax / bins)
+    double edge_rmax = 0.0;
+    int edge_nbins = 0;
+    std::vector<double> edge_cache;
     std::vector<PoolBlock> pool_idle;
     std::unordered_map<void *, PoolBlock> pool_live;
     cudaStream_t s_compute = nullptr;
