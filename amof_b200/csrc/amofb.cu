@@ -433,6 +433,11 @@ struct PairState {
     double cn_r2max = 0.0;
     // tiled path (pair_tiled.cuh)
     bool tiled = false, cn_wide = false;
+    // fp32 fast path (pair_tiled.cuh): host-evaluated certainty bands
+    bool f32_ok = false;
+    F32Params f32{};
+    float2 *d_cn_band = nullptr;
+    double f32_lmax = 128.0;
     PairTile *d_tiles = nullptr;
     int *d_ntiles = nullptr, *d_flags = nullptr;
     uint8_t *d_hard = nullptr;
@@ -451,9 +456,15 @@ static void pair_release(amofb_ctx *ctx) {
     cudaStreamSynchronize(ctx->s_compute);
     batcher_release(ctx, p->bt);
     pool_put(ctx, p->d_edge2); pool_put(ctx, p->d_cnthr2); pool_put(ctx, p->d_keyidx); pool_put(ctx, p->d_slabs); pool_put(ctx, p->d_hist);
-    pool_put(ctx, p->d_tiles); pool_put(ctx, p->d_ntiles); pool_put(ctx, p->d_flags); pool_put(ctx, p->d_hard);
+    pool_put(ctx, p->d_tiles); pool_put(ctx, p->d_ntiles); pool_put(ctx, p->d_flags); pool_put(ctx, p->d_hard); pool_put(ctx, p->d_cn_band);
     delete p;
     ctx->pair = nullptr;
+}
+
+static const void *tiled_kernel(bool has_cn, bool cn_wide, bool f32) {
+    if (!has_cn) return f32 ? (const void *)k_pair_tiled<false, false, true> : (const void *)k_pair_tiled<false, false, false>;
+    if (cn_wide) return f32 ? (const void *)k_pair_tiled<true, true, true> : (const void *)k_pair_tiled<true, true, false>;
+    return f32 ? (const void *)k_pair_tiled<true, false, true> : (const void *)k_pair_tiled<true, false, false>;
 }
 
 template <bool R, bool C, bool M>
@@ -573,19 +584,31 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
         size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
         size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 2048;     // driver reserve + the kernel's static shared memory
         if (per_block > budget) per_block = budget;
-        long long cap = per_block > fixed ? (long long)((per_block - fixed) / sizeof(SAtom)) : 0;
+        // the fp32 fast path needs 16 more bytes per staged atom; it is only worth having when its margin is small
+        double f32_margin = 1.0;
+        {
+            const double u = 5.9604644775390625e-08, dmax = sqrt(std::max(p->r2search, 0.0)) * 1.001 + 1e-6;
+            const double ddiff = 2.0 * p->f32_lmax * u + u * dmax;
+            f32_margin = 2.0 * (sqrt(3.0) * ddiff + 2.0 * u * dmax) / (rmax / (double)nbins) + (double)nbins * 1.0e-6 + 2.0e-4;
+        }
+        const bool want_f32 = TILE_F32 && f32_margin <= 0.05 && !env_int("AMOFB_NO_F32", 0);
+        const size_t per_atom = sizeof(SAtom) + (want_f32 ? sizeof(float4) : 0);
+        fixed += want_f32 ? sizeof(float2) * p->nkeys : 0;
+        long long cap = per_block > fixed ? (long long)((per_block - fixed) / per_atom) : 0;
         int cap_env = env_int("AMOFB_TILE_CAP", 0);
         if (cap_env > 0 && cap_env < cap) cap = cap_env;
         if (cap > 2000) cap = 2000;     // run lengths must stay below 2048 (magic-number divisions, 16-bit queue indices)
         if (cap >= 256) {
             p->tile_cap = (int)cap;
-            p->tile_smem = fixed + sizeof(SAtom) * (size_t)cap;
+            p->tile_smem = fixed + per_atom * (size_t)cap;
             int per_sm = 0;
             p->cn_wide = p->has_cn && p->cn_r2max > p->r2max;
-            const void *kfn = !p->has_cn ? (const void *)k_pair_tiled<false, false>
-                              : p->cn_wide ? (const void *)k_pair_tiled<true, true> : (const void *)k_pair_tiled<true, false>;
-            cudaError_t e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-            if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, TILE_THREADS, p->tile_smem);
+            cudaError_t e1 = cudaSuccess;
+            for (int f32 = 0; f32 < 2 && e1 == cudaSuccess; ++f32) {       // both flavours share the shared-memory size
+                const void *kfn = tiled_kernel(p->has_cn, p->cn_wide, f32 != 0);
+                e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+                if (e1 == cudaSuccess) { int n = 0; e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, TILE_THREADS, p->tile_smem); per_sm = f32 ? std::min(per_sm, n) : n; }
+            }
             if (e1 == cudaSuccess && per_sm >= 1) {
                 p->tiled = true;
                 p->tile_grid = ctx->num_sms * per_sm;
@@ -599,6 +622,42 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
                 if ((rc = dev_alloc(ctx, &p->d_flags, 1))) return fail(rc);
                 if ((rc = dev_alloc(ctx, &p->d_hard, p->hard_bytes))) return fail(rc);
                 cudaMemset(p->d_flags, 0, sizeof(int));
+#if TILE_F32
+                if (want_f32) {
+                    // error model of the fp32 path (see scan_run_f32), with a safety factor of 2 on the distance error
+                    const double u = 5.9604644775390625e-08;                    // 2^-24
+                    const double dmax = sqrt(std::max(p->r2search, 0.0)) * 1.001 + 1e-6;
+                    const double dcoord = p->f32_lmax * u;                      // one rounded local coordinate
+                    const double ddiff = 2.0 * dcoord + u * dmax;               // one coordinate difference
+                    auto E = [&](double d) { return 2.0 * (2.0 * sqrt(3.0) * d * ddiff * (1.0 + 4.0 * u) + 4.0 * u * d * d + 3.0 * ddiff * ddiff) + 1e-12; };
+                    auto fdown = [](double x) { float f = (float)x; while ((double)f > x) f = nextafterf(f, -INFINITY); return nextafterf(f, -INFINITY); };
+                    auto fup = [](double x) { float f = (float)x; while ((double)f < x) f = nextafterf(f, INFINITY); return nextafterf(f, INFINITY); };
+                    const double dr = rmax / (double)nbins;
+                    const double margin = 2.0 * (sqrt(3.0) * ddiff + 2.0 * u * dmax) / dr + (double)nbins * 1.0e-6 + 2.0e-4;
+                    if (margin <= 0.05) {
+                        F32Params &f = p->f32;
+                        const double rm = sqrt(p->r2max);
+                        f.r2max_lo = fdown(p->r2max - E(rm));
+                        f.r2max_hi = fup(p->r2max + E(rm));
+                        f.margin = (float)margin;
+                        std::vector<float2> band((size_t)p->nkeys, make_float2(0.f, 0.f));
+                        double cnhi = 0.0;
+                        for (int k = 0; k < p->nkeys; ++k)
+                            if (cnthr[k] > 0.0) {
+                                const double d = sqrt(cnthr[k]);
+                                band[k] = make_float2(fdown(cnthr[k] - E(d)), fup(cnthr[k] + E(d)));
+                                cnhi = std::max(cnhi, (double)band[k].y);
+                            }
+                        f.cn_hi = (float)cnhi;
+                        f.r2hi = std::max(f.r2max_hi, f.cn_hi);
+                        if ((rc = dev_alloc(ctx, &p->d_cn_band, band.size()))) return fail(rc);
+                        cudaMemcpy(p->d_cn_band, band.data(), sizeof(float2) * band.size(), cudaMemcpyHostToDevice);
+                        f.cn_band = p->d_cn_band;
+                        f.enabled = 1;
+                        p->f32_ok = true;
+                    }
+                }
+#endif
             } else cudaGetLastError();
         }
     }
@@ -684,19 +743,37 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 done += nf;
                 continue;
             }
+            // fp32 path: local coordinates must stay below f32_lmax -> bound the tile length along the column
+            int zlen_max = TILE_MAX_ZLEN;
+            bool f32_now = tiled && p->f32_ok;
+            for (int f = 0; f < nf && f32_now; ++f) {
+                const FrameGeom &g = s->h_geom[f];
+                double e[3], ext = 0.0;
+                for (int k = 0; k < 3; ++k) {
+                    e[k] = sqrt((g.cell[3 * k] * g.cell[3 * k] + g.cell[3 * k + 1] * g.cell[3 * k + 1]) + g.cell[3 * k + 2] * g.cell[3 * k + 2]) / g.nc[k];
+                    ext += (g.m[k] + 2) * e[k];
+                }
+                const double room = (p->f32_lmax - ext) / e[2];
+                if (!(room >= 1.0)) f32_now = false;
+                else zlen_max = std::min(zlen_max, (int)room);
+            }
+            if (!f32_now) zlen_max = TILE_MAX_ZLEN;
             if (tiled) {
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles, 0, sizeof(int) * 4, ctx->s_compute));
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_hard, 0, ncell_total, ctx->s_compute));
                 PlanArgs pl;
                 pl.geom = s->d_geom; pl.cell_start = s->d_cell_start; pl.tiles = p->d_tiles; pl.n_tiles = p->d_ntiles;
-                pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles;
+                pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles; pl.zlen_max = zlen_max;
                 k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(pl);      // one warp per column
                 TiledArgs ta;
                 ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;
                 ta.p.hard_mask = nullptr; ta.p.n_hard = nullptr;
-                if (!p->has_cn) k_pair_tiled<false, false><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
-                else if (p->cn_wide) k_pair_tiled<true, true><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
-                else k_pair_tiled<true, false><<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(ta);
+                ta.f = p->f32; ta.f.enabled = f32_now ? 1 : 0;
+                {
+                    void *kargs[] = {(void *)&ta};
+                    CUDA_TRY(ctx, cudaLaunchKernel(tiled_kernel(p->has_cn, p->cn_wide, f32_now), dim3(p->tile_grid), dim3(TILE_THREADS), kargs,
+                                                   p->tile_smem, ctx->s_compute));
+                }
                 ctx->launches += 2;
                 CUDA_TRY(ctx, cudaGetLastError());
                 a.hard_mask = p->d_hard;          // clean-up launch: only the home cells the plan could not tile
