@@ -239,6 +239,17 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 __device__ __forceinline__ void reds_inc(unsigned addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
 }
+// 32-bit shared addresses of the kernel's tables, derived once per kernel from an opaque base (the asm keeps the
+// compiler from re-materialising S2UR SR_CgaCtaId + ULEA chains next to every use)
+struct SmemAddr {
+    unsigned atoms, edge, cnthr, hist, cn, key;
+};
+__device__ __forceinline__ unsigned opaque_u32(unsigned v) {
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 // rdf_bin (pair.cuh) on a shared-memory threshold table given by its 32-bit shared address; margin > 0 path only
 __device__ __forceinline__ int rdf_bin_s(double d2, unsigned edge_addr, float inv_dr_f, float margin) {
     const int b = (int)fmaf(sqrt_approx((float)d2), inv_dr_f, -margin);
@@ -286,7 +297,7 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
                                          const double *__restrict__ s_cnthr, uint32_t *__restrict__ s_hist, uint32_t *__restrict__ s_cn,
                                          const uint16_t *__restrict__ s_key, HitQueue &hq, const SAtom &me, double Tx, double Ty, double Tz,
                                          int jb, int je, int G, int n_iter, int sub, bool active, int ism, int hidx, int lane,
-                                         unsigned lt_mask) {
+                                         unsigned lt_mask, const SmemAddr &sa) {
     const double r2search = a.r2search;
 #if TILE_QUEUE
     const unsigned long long who_hi = (unsigned long long)hidx << 16;
@@ -314,13 +325,8 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
     const double r2max = a.r2max, cn_r2max = a.cn_r2max;
     const float inv_dr_f = a.inv_dr_f, margin = a.bin_margin;
     const int nbins = a.nbins;
-    const uint16_t *krow = s_key + (int)(me.s & 0xff) * a.n_species;
-    const unsigned abase = (unsigned)__cvta_generic_to_shared(s_atoms);     // one register instead of re-deriving the window base
-    const unsigned edge_addr = (unsigned)__cvta_generic_to_shared(s_edge2);
-    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(s_hist);
-    const unsigned krow_addr = (unsigned)__cvta_generic_to_shared(krow);
-    const unsigned cnthr_addr = HAS_CN ? (unsigned)__cvta_generic_to_shared(s_cnthr) : 0u;
-    const unsigned cn_addr = HAS_CN ? (unsigned)__cvta_generic_to_shared(s_cn) : 0u;
+    const unsigned abase = sa.atoms, edge_addr = sa.edge, hist_addr = sa.hist, cnthr_addr = sa.cnthr, cn_addr = sa.cn;
+    const unsigned krow_addr = sa.key + 2u * (unsigned)((int)(me.s & 0xff) * a.n_species);
     const unsigned astep = (unsigned)G * 32u;
     const unsigned aend = abase + (unsigned)je * 32u;
     // AFTER: partners staged at or before me do not count (ism < 0: I am staged before this whole run -> nothing to skip)
@@ -520,6 +526,16 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     off = (off + 15) & ~(size_t)15;
     FlatRun *s_runs = reinterpret_cast<FlatRun *>(smem_raw + off);         off += sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32);
     uint16_t *s_key = reinterpret_cast<uint16_t *>(smem_raw + off);
+    SmemAddr sa;
+    {
+        const unsigned sb = opaque_u32((unsigned)__cvta_generic_to_shared(smem_raw));
+        sa.atoms = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_atoms) - smem_raw);
+        sa.edge = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_edge2) - smem_raw);
+        sa.cnthr = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_cnthr) - smem_raw);
+        sa.hist = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_hist) - smem_raw);
+        sa.cn = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_cn) - smem_raw);
+        sa.key = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_key) - smem_raw);
+    }
     __shared__ FrameGeom s_geom;
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_rowimg[TILE_MAX_ROWS];        // per staged row: image (s0 | s1 << 16) of its column
@@ -793,7 +809,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
             if (nh == 0) continue;
             const int img01 = s_rowimg[rr];                               // image of the row's column, prepared per tile
             const int s0 = (int)(short)(img01 & 0xffff), s1 = img01 >> 16;
-            const double fs0 = (double)s0, fs1 = (double)s1;
             const bool home_row = (r == 0);
             const int own_off = home_row ? s_off[rr * V + hz + m2] : 0;   // position of the home cell inside row 0
             for (int h0 = 0; h0 < nh; h0 += 32) {
@@ -825,15 +840,15 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
                         continue;
                     }
                     if ((s0 | s1 | s2) != 0) {
-                        const double fs2 = (double)s2;
+                        const double fs0 = (double)s0, fs1 = (double)s1, fs2 = (double)s2;
                         const double Tx = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
                         const double Ty = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
                         const double Tz = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
-                        if (after_me) scan_run<HAS_CN, CN_WIDE, true, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
-                        else scan_run<HAS_CN, CN_WIDE, true, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        if (after_me) scan_run<HAS_CN, CN_WIDE, true, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask, sa);
+                        else scan_run<HAS_CN, CN_WIDE, true, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask, sa);
                     } else {
-                        if (after_me) scan_run<HAS_CN, CN_WIDE, false, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
-                        else scan_run<HAS_CN, CN_WIDE, false, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask);
+                        if (after_me) scan_run<HAS_CN, CN_WIDE, false, true>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask, sa);
+                        else scan_run<HAS_CN, CN_WIDE, false, false>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, jb, je, G, n_iter, sub, active, ism, hidx, lane, lt_mask, sa);
                     }
                     d2 += len;
                 }

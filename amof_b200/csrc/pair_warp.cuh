@@ -53,6 +53,15 @@ __global__ void __launch_bounds__(WARP_THREADS, 2) k_pair_warp(WarpArgs wa) {
     for (int k = threadIdx.x; k < S * S; k += blockDim.x) s_key[k] = a.keyidx[k];
     __syncthreads();
 
+    SmemAddr sa;
+    {
+        const unsigned sb = opaque_u32((unsigned)__cvta_generic_to_shared(smem_raw));
+        sa.edge = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_edge2) - smem_raw);
+        sa.cnthr = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_cnthr) - smem_raw);
+        sa.hist = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_hist) - smem_raw);
+        sa.key = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_key) - smem_raw);
+        sa.atoms = 0u; sa.cn = 0u;      // per warp / per chunk, set below
+    }
     SAtom *buf = s_buf + warp * 2 * WCHUNK;
     uint32_t *s_cn = s_cn_all + warp * a.nkeys;
     HitQueue hq;                                   // unused in the direct mode; keeps scan_run's signature
@@ -142,6 +151,8 @@ __global__ void __launch_bounds__(WARP_THREADS, 2) k_pair_warp(WarpArgs wa) {
                 if (have_next) issue_loads();
                 // scan the current chunk
                 const SAtom *cb = buf + cur * WCHUNK;
+                sa.atoms = (unsigned)__cvta_generic_to_shared(cb);
+                sa.cn = (unsigned)__cvta_generic_to_shared(s_cn);
                 const int G2 = G_;
                 const int n_iter = (int)(((unsigned)(c_n + G2 - 1) * g_magic) >> 16);
                 const int ism = iabs - c_jb;                   // chunk-relative index of "me" (meaningful when c_after)
@@ -150,11 +161,11 @@ __global__ void __launch_bounds__(WARP_THREADS, 2) k_pair_warp(WarpArgs wa) {
                     const double Tx = (fs0 * G.cell[0] + fs1 * G.cell[3]) + fs2 * G.cell[6];
                     const double Ty = (fs0 * G.cell[1] + fs1 * G.cell[4]) + fs2 * G.cell[7];
                     const double Tz = (fs0 * G.cell[2] + fs1 * G.cell[5]) + fs2 * G.cell[8];
-                    if (c_after) scan_run<HAS_CN, true, true, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
-                    else scan_run<HAS_CN, true, true, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
+                    if (c_after) scan_run<HAS_CN, true, true, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u, sa);
+                    else scan_run<HAS_CN, true, true, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, Tx, Ty, Tz, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u, sa);
                 } else {
-                    if (c_after) scan_run<HAS_CN, true, false, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
-                    else scan_run<HAS_CN, true, false, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u);
+                    if (c_after) scan_run<HAS_CN, true, false, true>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u, sa);
+                    else scan_run<HAS_CN, true, false, false>(a, cb, s_edge2, s_cnthr, s_hist, s_cn, s_key, hq, me, 0.0, 0.0, 0.0, 0, c_n, G2, n_iter, sub, active, ism, 0, lane, 0u, sa);
                 }
                 __syncwarp();
                 cur ^= 1;
