@@ -387,16 +387,14 @@ struct __align__(16) FlatRun {
     int jofs;        // staged index = flat index + jofs; bit 30 of kbeg set: the run starts with the home cell itself
 };
 
-template <bool HAS_CN>
-__device__ __forceinline__ void scan_flat(const PairArgs &a, const SAtom *__restrict__ s_atoms, const double *__restrict__ s_edge2,
-                                          const double *__restrict__ s_cnthr, uint32_t *__restrict__ s_hist, uint32_t *__restrict__ s_cn,
-                                          const uint16_t *__restrict__ s_key, const FlatRun *__restrict__ runs, int total,
+template <bool HAS_CN, bool CN_WIDE>
+__device__ __forceinline__ void scan_flat(const PairArgs &a, const SmemAddr &sa, const FlatRun *__restrict__ runs, int total,
                                           const SAtom &me, int sub, int G, int ism) {
     const double r2search = a.r2search, r2max = a.r2max, cn_r2max = a.cn_r2max;
     const float inv_dr_f = a.inv_dr_f, margin = a.bin_margin;
     const int nbins = a.nbins;
-    const uint16_t *krow = s_key + (int)(me.s & 0xff) * a.n_species;
-    const unsigned abase = (unsigned)__cvta_generic_to_shared(s_atoms);
+    const unsigned krow_addr = sa.key + 2u * (unsigned)((int)(me.s & 0xff) * a.n_species);
+    const unsigned abase = sa.atoms;
     int e = 0;
     FlatRun cur = runs[0];
     int kend = runs[1].kbeg & 0x3fffffff;
@@ -417,12 +415,12 @@ __device__ __forceinline__ void scan_flat(const PairArgs &a, const SAtom *__rest
         const double dz = (oz - me.z) + cur.Tz;
         const double dd = (dx * dx + dy * dy) + dz * dz;
         if (dd < r2search && j > jskip) {
-            const int key = krow[lds_species(addr)];
-            if (!HAS_CN || dd < r2max) {          // without cutoffs r2search == r2max
-                const int b = rdf_bin(dd, s_edge2, inv_dr_f, margin, nbins);
-                atomicAdd(&s_hist[key * nbins + b], 1u);
+            const int key = lds_u16(krow_addr + 2u * (unsigned)lds_species(addr));
+            if (!CN_WIDE || dd < r2max) {
+                const int b = rdf_bin_s(dd, sa.edge, inv_dr_f, margin);
+                reds_inc(sa.hist + 4u * (unsigned)(key * nbins + b));
             }
-            if (HAS_CN && dd < cn_r2max && dd < s_cnthr[key]) atomicAdd(&s_cn[key], 1u);
+            if (HAS_CN && dd < cn_r2max && dd < lds_f64(sa.cnthr + 8u * (unsigned)key)) reds_inc(sa.cn + 4u * (unsigned)key);
         }
     }
 }
@@ -792,7 +790,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
                         const int il = (int)(((unsigned)lane * g_magic) >> 16), sub = lane - il * G;
                         if (il < ng) {
                             const SAtom me = s_atoms[hb + h0 + il];
-                            scan_flat<HAS_CN>(a, s_atoms, s_edge2, s_cnthr, s_hist, s_cn, s_key, runs, total, me, sub, G, own_off + h0 + il);
+                            scan_flat<HAS_CN, CN_WIDE>(a, sa, runs, total, me, sub, G, own_off + h0 + il);
                         }
                     }
                 }
