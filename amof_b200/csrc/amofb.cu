@@ -5,6 +5,7 @@
 #include "pair.cuh"
 #include "pair_tiled.cuh"
 #include "pair_warp.cuh"
+#include "pair_pipe.cuh"
 #include "bad.cuh"
 #include "msd.cuh"
 
@@ -433,6 +434,7 @@ struct PairState {
     double cn_r2max = 0.0;
     // tiled path (pair_tiled.cuh)
     bool tiled = false, cn_wide = false;
+    bool pipe = false;            // producer/consumer kernel (pair_pipe.cuh) instead of k_pair_tiled
     // fp32 fast path (pair_tiled.cuh): host-evaluated certainty bands
     bool f32_ok = false;
     F32Params f32{};
@@ -465,6 +467,11 @@ static const void *tiled_kernel(bool has_cn, bool cn_wide, bool f32) {
     if (!has_cn) return f32 ? (const void *)k_pair_tiled<false, false, true> : (const void *)k_pair_tiled<false, false, false>;
     if (cn_wide) return f32 ? (const void *)k_pair_tiled<true, true, true> : (const void *)k_pair_tiled<true, true, false>;
     return f32 ? (const void *)k_pair_tiled<true, false, true> : (const void *)k_pair_tiled<true, false, false>;
+}
+
+static const void *pipe_kernel(bool has_cn, bool cn_wide) {
+    if (!has_cn) return (const void *)k_pair_pipe<false, false>;
+    return cn_wide ? (const void *)k_pair_pipe<true, true> : (const void *)k_pair_pipe<true, false>;
 }
 
 template <bool R, bool C, bool M>
@@ -595,16 +602,29 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
         const size_t per_atom = sizeof(SAtom) + (want_f32 ? sizeof(float4) : 0);
         fixed += want_f32 ? sizeof(float2) * p->nkeys : 0;
         long long cap = per_block > fixed ? (long long)((per_block - fixed) / per_atom) : 0;
+        // producer/consumer kernel: one block per SM, PIPE_STAGES tile buffers
+        const bool want_pipe = !want_f32 && env_int("AMOFB_PAIR_PIPE", 0) != 0;
+        if (want_pipe) {
+            const size_t pipe_fixed = pipe_layout(0, nbins, p->nkeys, S, p->has_cn).total;
+            const size_t pipe_budget = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;   // static: meta, mbarriers, counters
+            cap = pipe_budget > pipe_fixed ? (long long)((pipe_budget - pipe_fixed) / (sizeof(SAtom) * PIPE_STAGES)) : 0;
+        }
         int cap_env = env_int("AMOFB_TILE_CAP", 0);
         if (cap_env > 0 && cap_env < cap) cap = cap_env;
         if (cap > 2000) cap = 2000;     // run lengths must stay below 2048 (magic-number divisions, 16-bit queue indices)
         if (cap >= 256) {
             p->tile_cap = (int)cap;
-            p->tile_smem = fixed + per_atom * (size_t)cap;
+            p->tile_smem = want_pipe ? (size_t)pipe_layout((int)cap, nbins, p->nkeys, S, p->has_cn).total : fixed + per_atom * (size_t)cap;
             int per_sm = 0;
             p->cn_wide = p->has_cn && p->cn_r2max > p->r2max;
             cudaError_t e1 = cudaSuccess;
-            for (int f32 = 0; f32 < 2 && e1 == cudaSuccess; ++f32) {       // both flavours share the shared-memory size
+            if (want_pipe) {
+                const void *kfn = pipe_kernel(p->has_cn, p->cn_wide);
+                e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+                if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PIPE_THREADS, p->tile_smem);
+                if (e1 == cudaSuccess && per_sm >= 1) { p->pipe = true; per_sm = 1; }
+            }
+            for (int f32 = 0; f32 < 2 && e1 == cudaSuccess && !want_pipe; ++f32) {       // both flavours share the shared-memory size
                 const void *kfn = tiled_kernel(p->has_cn, p->cn_wide, f32 != 0);
                 e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
                 if (e1 == cudaSuccess) { int n = 0; e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, TILE_THREADS, p->tile_smem); per_sm = f32 ? std::min(per_sm, n) : n; }
@@ -771,8 +791,12 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 ta.f = p->f32; ta.f.enabled = f32_now ? 1 : 0;
                 {
                     void *kargs[] = {(void *)&ta};
-                    CUDA_TRY(ctx, cudaLaunchKernel(tiled_kernel(p->has_cn, p->cn_wide, f32_now), dim3(p->tile_grid), dim3(TILE_THREADS), kargs,
-                                                   p->tile_smem, ctx->s_compute));
+                    if (p->pipe)
+                        CUDA_TRY(ctx, cudaLaunchKernel(pipe_kernel(p->has_cn, p->cn_wide), dim3(p->tile_grid), dim3(PIPE_THREADS), kargs,
+                                                       p->tile_smem, ctx->s_compute));
+                    else
+                        CUDA_TRY(ctx, cudaLaunchKernel(tiled_kernel(p->has_cn, p->cn_wide, f32_now), dim3(p->tile_grid), dim3(TILE_THREADS), kargs,
+                                                       p->tile_smem, ctx->s_compute));
                 }
                 ctx->launches += 2;
                 CUDA_TRY(ctx, cudaGetLastError());

@@ -310,6 +310,160 @@ __global__ void __launch_bounds__(MSD_THREADS) k_msd_window(const double *__rest
     for (int i = threadIdx.x; i < S * nw; i += blockDim.x) partial[(size_t)blockIdx.x * S * nw + i] = s_acc[i];
 }
 
+// ---- window MSD, window lengths in arithmetic progression -------------------------------------------------
+// WindowMsd always asks for m = 0, D, 2D, ... (msd.py:176-178: window = arange(0, max_time, delta_time)).  k_msd_window
+// reads one R_{k-m} from shared memory per frame pair and is bound by the shared-memory pipe (ncu: 85 % busy, the
+// 24-byte stride costing a 2-way bank conflict).  With lags that are multiples of D a thread can keep a TILE of KB
+// frames k_i = b + i*D in registers and walk the partners j_u = b - (wlo + u)*D: the pair (k_i, j_u) has lag
+// (wlo + u + i)*D, i.e. it belongs to window wlo + u + i, so one shared-memory read of R_j feeds KB pairs.
+//   * the windows of a pass are split into NG groups of <= MSD_AP_NWT; a warp belongs to ONE group and holds only that
+//     group's sums in registers (8 doubles instead of 32 -> three times the warps per SM); every group walks all tasks;
+//   * full super-rows: frames [1 + s*KB*D, 1 + (s+1)*KB*D) all exist -> task (s, r) owns k_i = 1 + s*KB*D + r + i*D;
+//     the remaining frames (fewer than KB*D) are handled one frame per task (KB = 1);
+//   * a partner before frame 1 (the reference starts at k = m + 1, msd.py:197) is clamped and weighted by 0.0 through
+//     the accumulating FMA (fma(1.0, d2, acc) == acc + d2 bit for bit).
+// Everything is fully unrolled, so the window sums stay in registers under static indices.
+#ifndef MSD_AP_KB
+#define MSD_AP_KB 4
+#endif
+#define MSD_AP_NWT_MAX 13       // window sums per thread: instantiated for 5, 7, 9, 11, 13 (128 registers at 13)
+#ifndef MSD_AP_THREADS
+#define MSD_AP_THREADS 512
+#endif
+
+// sm: the staged series as three arrays x[tp], y[tp], z[tp] (consecutive threads -> consecutive words: no bank conflict)
+// EDGE: some partner of this tile lies before frame 1 (the reference starts at k = m + 1, msd.py:197); partners only move
+// backwards with u, so the lane simply stops at the first one that does not exist.
+template <int KB, int NWT, bool EDGE>
+__device__ __forceinline__ void msd_ap_tile(const double *__restrict__ sm, int tp, int b, int delta, int lag0, double (&acc)[NWT]) {
+    double kx[KB], ky[KB], kz[KB];
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+        const double *q = sm + (b + i * delta);
+        kx[i] = q[0]; ky[i] = q[tp]; kz[i] = q[2 * tp];
+    }
+#pragma unroll
+    for (int u = -(KB - 1); u < NWT; ++u) {
+        const int j0 = b - lag0 - u * delta;
+        if (EDGE && j0 < 1) break;
+        const double *q = sm + j0;
+        const double jx = q[0], jy = q[tp], jz = q[2 * tp];
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+            const int w = u + i;
+            if (w >= 0 && w < NWT) {
+                const double dx = kx[i] - jx, dy = ky[i] - jy, dz = kz[i] - jz;
+                acc[w] += __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
+            }
+        }
+    }
+}
+
+// ng groups of NWT windows per pass (ng * NWT windows; those beyond nw are formed and dropped); blockDim.x = 32 * ng * (warps per group)
+template <int KB, int NWT>
+__global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *__restrict__ P, const uint8_t *__restrict__ species, int n, int T,
+                                                                  int delta, int nw, int ng, int S, double *__restrict__ partial) {
+    constexpr int nwt = NWT;
+    extern __shared__ double sm[];
+    const int tp = (T + 1) & ~1;                            // padded series length (keeps y[] and z[] 16-byte aligned)
+    double *s_acc = sm + 3 * (size_t)tp;                    // [S][nw] block accumulators (after the staged series)
+    double *s_red = s_acc + (size_t)S * nw;                 // [nwarp][NWT]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int grp = warp % ng, wpg = nwarp / ng;            // my window group; warps per group
+    const int tg = (warp / ng) * 32 + lane, gs = wpg * 32;  // my index among the group's threads
+    for (int i = threadIdx.x; i < S * nw; i += blockDim.x) s_acc[i] = 0.0;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int a_lo = blockIdx.x * per, a_hi = min(n, a_lo + per);
+    const int span = KB * delta;
+    const int nsr = (T - 1) / span;                         // full super-rows over k = 1 .. T-1
+    const int ntask = nsr * delta;
+    const int k_rem = 1 + nsr * span;                       // first frame of the remainder
+    for (int w0 = 0; w0 < nw; w0 += ng * nwt) {
+        const int wlo = w0 + grp * nwt;                     // first window of my group in this pass
+        const bool mine = wlo < nw;                         // my group has at least one requested window
+        const int lag0 = wlo * delta;
+        const int lag_far = lag0 + (NWT - 1) * delta;       // the longest lag of my group
+        double acc[NWT];
+#pragma unroll
+        for (int w = 0; w < NWT; ++w) acc[w] = 0.0;
+        int cur_sp = -1;
+        for (int a = a_lo; a <= a_hi; ++a) {
+            const int sp = a < a_hi ? (int)species[a] : -2;
+            if (sp != cur_sp) {
+                if (cur_sp >= 0) {                          // species changed (or done): reduce the register sums
+#pragma unroll
+                    for (int w = 0; w < NWT; ++w) {
+                        double v = acc[w];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                        if (lane == 0) s_red[warp * NWT + w] = v;
+                        acc[w] = 0.0;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < ng * nwt) {           // thread -> (group, window of the group); warps of a group in order
+                        const int g = threadIdx.x / nwt, w = threadIdx.x - g * nwt, wi = w0 + g * nwt + w;
+                        if (wi < nw) {
+                            double t = 0.0;
+                            for (int q = 0; q < wpg; ++q) t += s_red[(q * ng + g) * NWT + w];
+                            s_acc[cur_sp * nw + wi] += t;
+                        }
+                    }
+                    __syncthreads();
+                }
+                cur_sp = sp;
+            }
+            if (a >= a_hi) break;
+            const double *p = P + (size_t)a * T * 3;
+            __syncthreads();                                // everyone finished the previous atom
+            // stage the series AoS -> SoA: wide loads, 4 in flight per thread; element e of the stream is component
+            // e % 3 of frame e / 3
+            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                const double2 *p2 = reinterpret_cast<const double2 *>(p);
+                const int n2 = (3 * T) >> 1;
+                for (int i0 = threadIdx.x; i0 < n2; i0 += 8 * blockDim.x) {
+                    double2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (i0 + u * blockDim.x < n2) v[u] = __ldg(p2 + i0 + u * blockDim.x);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * blockDim.x;
+                        if (i < n2) {
+                            const unsigned e = 2u * (unsigned)i, f0 = e / 3u, c0 = e - 3u * f0;
+                            const unsigned f1 = c0 == 2u ? f0 + 1u : f0, c1 = c0 == 2u ? 0u : c0 + 1u;
+                            sm[c0 * tp + f0] = v[u].x;
+                            sm[c1 * tp + f1] = v[u].y;
+                        }
+                    }
+                }
+                if ((3 * T) & 1) { if (threadIdx.x == 0) sm[2 * tp + (T - 1)] = p[3 * T - 1]; }
+            } else {
+                for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) { const int f = i / 3; sm[(i - 3 * f) * tp + f] = p[i]; }
+            }
+            if (a + 1 < a_hi) {                             // pull the next series into L2 while this one is worked on
+                const char *nx = reinterpret_cast<const char *>(p + (size_t)T * 3);
+                const int nlines = (3 * T * 8 + 127) >> 7;
+                for (int i = threadIdx.x; i < nlines; i += blockDim.x)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + ((size_t)i << 7)));
+            }
+            __syncthreads();
+            if (mine) {
+                for (int q = tg; q < ntask; q += gs) {
+                    const int s = q / delta, r = q - s * delta;
+                    const int b = 1 + s * span + r;
+                    if (b - lag_far >= 1) msd_ap_tile<KB, NWT, false>(sm, tp, b, delta, lag0, acc);
+                    else msd_ap_tile<KB, NWT, true>(sm, tp, b, delta, lag0, acc);
+                }
+                for (int k = k_rem + tg; k < T; k += gs) {
+                    if (k - lag_far >= 1) msd_ap_tile<1, NWT, false>(sm, tp, k, delta, lag0, acc);
+                    else msd_ap_tile<1, NWT, true>(sm, tp, k, delta, lag0, acc);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * nw; i += blockDim.x) partial[(size_t)blockIdx.x * S * nw + i] = s_acc[i];
+}
+
 // ---- DirectMsd ----------------------------------------------------------------------------------------
 // one thread per atom, sequential in t; overwrites P[a][t].x with |r_t - r_0|^2 (P[a][0].x = 0)
 __global__ void __launch_bounds__(128) k_msd_direct(double *__restrict__ P, const MsdGeom *__restrict__ geom, int n, int T) {

@@ -208,17 +208,70 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
         p->prepared = true;
     }
     if (n_window == 0) return AMOFB_OK;
-    const int S = p->S, threads = MSD_THREADS, nwarp = threads / 32;
+    const int S = p->S;
+    int threads = MSD_THREADS;
+    // window lengths 0, D, 2D, ... (what WindowMsd always asks for, msd.py:176-178) -> register-tiled kernel
+    int ap_delta = 0;
+    if (n_window >= 2 && window[0] == 0 && window[1] > 0 && !env_int("AMOFB_MSD_NO_AP", 0)) {
+        ap_delta = window[1];
+        for (int w = 2; w < n_window && ap_delta; ++w)
+            if ((long long)window[w] != (long long)w * ap_delta) ap_delta = 0;
+        if (ap_delta && (long long)MSD_AP_KB * ap_delta >= p->T) ap_delta = 0;      // not a single full tile: nothing to gain
+    }
+    int ap_ng = 1, ap_nwt = 1;
+    const int force_ng = env_int("AMOFB_MSD_AP_NG", 0), force_wpg = env_int("AMOFB_MSD_AP_WPG", 0), force_nwt = env_int("AMOFB_MSD_AP_NWT", 0);
+    if (ap_delta) {
+        // groups of <= MSD_AP_NWT windows bound to warps, and the block size that wastes the fewest thread slots:
+        // efficiency = (balance of the windows over the groups) x (fill of the last round of tasks)
+        const int span = MSD_AP_KB * ap_delta, nsr = (p->T - 1) / span;
+        const long long ntask = (long long)nsr * ap_delta, rem = (p->T - 1) - (long long)nsr * span;
+        const int max_warps = MSD_AP_THREADS / 32;
+        double best = -1.0;
+        for (int nwt = 5; nwt <= MSD_AP_NWT_MAX; nwt += 2) {
+            if (force_nwt > 0 && nwt != force_nwt) continue;
+            for (int ng = 1; ng <= max_warps; ++ng) {
+                if (force_ng > 0 && ng != force_ng) continue;
+                if (ng > 1 && (ng - 1) * nwt >= n_window) break;          // a group without a single requested window
+                const int passes = (n_window + ng * nwt - 1) / (ng * nwt);
+                for (int wpg = 1; wpg * ng <= max_warps; ++wpg) {
+                    if (force_wpg > 0 && wpg != force_wpg) continue;
+                    const int gs = 32 * wpg;
+                    const double slots = (double)((ntask + gs - 1) / gs) * MSD_AP_KB + (double)((rem + gs - 1) / gs);
+                    const double fill = ((double)ntask * MSD_AP_KB + (double)rem) / (slots * gs);
+                    const double balance = (double)n_window / ((double)passes * ng * nwt);
+                    // resident warps hide the FP64 latency: below 3/4 of the warp budget the score drops in proportion
+                    const double occ = std::min(1.0, (double)(wpg * ng) / (0.75 * max_warps));
+                    // frame pairs formed per shared-memory read: below ~2.2 the shared-memory pipe, not FP64, sets the pace
+                    const double ppl = (double)(MSD_AP_KB * nwt) / (double)(2 * MSD_AP_KB + nwt - 1);
+                    const double eff = fill * balance * occ * std::min(1.0, ppl / 2.2);
+                    if (eff > best + 1e-9) { best = eff; threads = 32 * wpg * ng; ap_ng = ng; ap_nwt = nwt; }
+                }
+            }
+        }
+    }
+    const int nwarp = threads / 32;
     int *d_window = nullptr;
     double *d_partial = nullptr;
-    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)MSD_NW * nwarp);
-    size_t smem_full = sizeof(double) * (3 * (size_t)p->T + 1) + extra;
+    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)MSD_NW * (size_t)std::max(MSD_AP_THREADS / 32, nwarp));
+    size_t smem_full = sizeof(double) * (3 * (size_t)p->T + 4) + extra;
     size_t budget = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;
     bool use_smem = smem_full <= budget && !env_int("AMOFB_MSD_NO_SMEM", 0);
+    if (!use_smem) ap_delta = 0;
     size_t smem = use_smem ? smem_full : extra;
     if (extra > budget) return amofb_fail(ctx, AMOFB_ERR_ARG, "too many window lengths (%d) for one pass", n_window);
     int per_sm = 1;
-    if (use_smem) {
+    const void *ap_kernel = nullptr;
+    if (ap_delta) {
+        switch (ap_nwt) {
+            case 5: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 5>; break;
+            case 7: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 7>; break;
+            case 9: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 9>; break;
+            case 11: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 11>; break;
+            default: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 13>; ap_nwt = 13; break;
+        }
+        CUDA_TRY(ctx, cudaFuncSetAttribute(ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ap_kernel, threads, smem));
+    } else if (use_smem) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_msd_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msd_window<true>, threads, smem));
     } else {
@@ -233,7 +286,12 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     std::vector<double> part((size_t)grid * S * n_window);
     cudaError_t e = cudaMemcpyAsync(d_window, window, sizeof(int) * n_window, cudaMemcpyHostToDevice, ctx->s_compute);
     if (e == cudaSuccess) {
-        if (use_smem) k_msd_window<true><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);
+        if (ap_delta) {
+            const double *a_P = p->d_P; const uint8_t *a_sp = p->d_species;
+            int a_n = p->n, a_T = p->T, a_S = S;
+            void *kargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_n, (void *)&a_T, (void *)&ap_delta, (void *)&n_window, (void *)&ap_ng, (void *)&a_S, (void *)&d_partial};
+            e = cudaLaunchKernel(ap_kernel, dim3(grid), dim3(threads), kargs, smem, ctx->s_compute);
+        } else if (use_smem) k_msd_window<true><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);
         else k_msd_window<false><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);
         ctx->launches += 1;
         e = cudaGetLastError();
