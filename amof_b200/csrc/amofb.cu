@@ -266,9 +266,8 @@ struct Batcher {
     double rcut = 0.0;
     int cell_div = 1;
     uint8_t *d_species = nullptr;
-    uint8_t *d_species_flag = nullptr;   // optional centre compaction (bond angles)
-    uint32_t *d_centres = nullptr;
-    int *d_ncentres = nullptr;
+    uint8_t *d_species_keep = nullptr;   // optional species filter of the cell list (bond angles)
+    int n_keep = 0;                      // atoms per frame that pass it (= n_atoms without a filter)
     BatchSlot slot[2];
     int next = 0;
     int64_t frames_seen = 0;
@@ -285,13 +284,14 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
     }
-    pool_put(ctx, b.d_species); pool_put(ctx, b.d_species_flag); pool_put(ctx, b.d_centres); pool_put(ctx, b.d_ncentres);
-    b.d_species = nullptr; b.d_species_flag = nullptr; b.d_centres = nullptr; b.d_ncentres = nullptr;
+    pool_put(ctx, b.d_species); pool_put(ctx, b.d_species_keep);
+    b.d_species = nullptr; b.d_species_keep = nullptr;
 }
 
 static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *species, double rcut, int cell_div,
                         int per_frame_out) {
     b.n_atoms = n_atoms;
+    b.n_keep = n_atoms;
     b.rcut = rcut;
     b.cell_div = cell_div;
     b.per_frame_out = per_frame_out;
@@ -369,8 +369,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.raw = raw; pa.geom = s.d_geom; pa.species = b.d_species;
     pa.cell_count = s.d_cell_count; pa.cell_start = s.d_cell_start; pa.cid = s.d_cid; pa.rank = s.d_rank;
     pa.sorted = s.d_sorted; pa.n_atoms = b.n_atoms; pa.n_frames = nf;
-    pa.species_flag = b.d_species_flag; pa.centres = b.d_centres; pa.n_centres = b.d_ncentres;
-    if (b.d_species_flag) CUDA_TRY(ctx, cudaMemsetAsync(b.d_ncentres, 0, sizeof(int), ctx->s_compute));
+    pa.species_keep = b.d_species_keep;
     long long total = (long long)nf * b.n_atoms;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;

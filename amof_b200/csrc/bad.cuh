@@ -1,7 +1,7 @@
 // bad.cuh -- bond-angle triplet kernel (K4 of SURVEY.md 2.1).
 //
-// One thread owns one centre atom (from the centre list k_cell_scatter compacts) of the cell-sorted frame: it walks the FULL stencil, keeps the unit vectors of
-// every neighbour under the pair cutoffs (P5), then for each requested (A, B) triple enumerates the unordered
+// One thread owns one centre atom of the cell-sorted frame: it walks the FULL stencil, keeps the unit vectors of every
+// neighbour under the pair cutoffs (P5), then for each requested (A, B) triple enumerates the unordered
 // pairs of its B-neighbours.  The angle itself is never formed on the device: x = u_p . u_q is computed in fp64
 // in the oracle's operation order (P6) and located in a table of thresholds on -x that the host bisected with its
 // own libm acos and the np.histogram edge rule (P7), so the bin is the one the CPU path takes, bit for bit,
@@ -23,8 +23,7 @@ struct BadArgs {
     unsigned long long *hist;     // [n_triples][AMOFB_BAD_MAX_CN+1][nbins]
     unsigned long long *dropped;  // [n_triples]
     int *flags;                   // bit 0: neighbour overflow, bit 1: cn > AMOFB_BAD_MAX_CN
-    const uint32_t *centres;      // batch-wide sorted indices (f*N + i) of the centre atoms
-    const int *n_centres;
+    int n_keep;                   // atoms per frame in the (species-filtered) cell list
     unsigned long long centre_mask[AMOFB_MAX_SPECIES];   // triples whose A matches this species
     double r2search;
     float inv_dtheta_f;
@@ -41,14 +40,14 @@ __device__ __forceinline__ int bad_bin(double t, const double *__restrict__ tthr
     return k;
 }
 
-// One THREAD per centre, taken from the compacted centre list that k_cell_scatter filled (atoms whose species is the A
-// of some triple: a few percent of a ZIF frame), so warps are full of centres instead of ~2 centres among 32 atoms.
+// One THREAD per atom of the cell-sorted frame, in sorted order: the cell list only holds the species that appear in
+// the cutoff matrix (PrepArgs::species_keep), so nearly every thread is a centre, and neighbouring threads sit in the
+// same or adjacent cells -- their cell_start[] and candidate reads hit the same lines.
 __global__ void __launch_bounds__(128) k_bad(BadArgs a) {
     const long long t_id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t_id >= (long long)*a.n_centres) return;
-    const long long g = a.centres[t_id];
-    const int f = (int)(g / a.n_atoms);
-    const int i = (int)(g - (long long)f * a.n_atoms);
+    if (t_id >= (long long)a.n_frames * a.n_keep) return;
+    const int f = (int)(t_id / a.n_keep);
+    const int i = (int)(t_id - (long long)f * a.n_keep);
     const SAtom *fr = a.sorted + (long long)f * a.n_atoms;
     const SAtom me = load_satom(fr + i);
     const int si = (int)(me.s & 0xff);

@@ -129,13 +129,18 @@ extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const
     int cell_div = env_int("AMOFB_BAD_CELL_DIV", 1);
     if (cell_div < 1) cell_div = 1;
     if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, 0))) return fail(rc);
-    {   // centre compaction: the cell-list scatter appends every atom whose species is the A of some triple
-        uint8_t flag[AMOFB_MAX_SPECIES];
-        for (int s = 0; s < AMOFB_MAX_SPECIES; ++s) flag[s] = p->centre_mask[s] != 0ull;
-        if ((rc = dev_alloc(ctx, &p->bt.d_species_flag, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
-        if ((rc = dev_alloc(ctx, &p->bt.d_centres, (size_t)p->bt.cap_frames * std::max(n_atoms, 1)))) return fail(rc);
-        if ((rc = dev_alloc(ctx, &p->bt.d_ncentres, 1))) return fail(rc);
-        cudaMemcpy(p->bt.d_species_flag, flag, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice);
+    {   // species filter: an atom whose species has no positive cutoff with any species can neither be a centre with
+        // neighbours nor a neighbour, so it never enters the cell list (ZIF-4 'Zn-N': 71 % of the atoms drop out)
+        uint8_t keep[AMOFB_MAX_SPECIES];
+        memset(keep, 0, sizeof keep);
+        for (int x = 0; x < S; ++x)
+            for (int y = 0; y < S; ++y)
+                if (cutoff[x * S + y] > 0.0) keep[x] = 1;
+        int n_keep = 0;
+        for (int i = 0; i < n_atoms; ++i) n_keep += keep[species[i]];
+        p->bt.n_keep = n_keep;
+        if ((rc = dev_alloc(ctx, &p->bt.d_species_keep, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
+        cudaMemcpy(p->bt.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice);
     }
     const size_t hist_n = (size_t)n_triples * (AMOFB_BAD_MAX_CN + 1) * nbins;
     if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
@@ -186,14 +191,14 @@ static int bad_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool o
         a.sorted = s->d_sorted; a.geom = s->d_geom; a.cell_start = s->d_cell_start;
         a.cn_thr2 = p->d_cnthr2; a.keyidx = p->d_keyidx; a.triples = p->d_triples; a.tthr = p->d_tthr;
         a.hist = p->d_hist; a.dropped = p->d_dropped; a.flags = p->d_flags;
-        a.centres = b.d_centres; a.n_centres = b.d_ncentres;
+        a.n_keep = b.n_keep;
         memcpy(a.centre_mask, p->centre_mask, sizeof a.centre_mask);
         a.r2search = p->r2search; a.inv_dtheta_f = (float)(1.0 / p->dtheta);
         a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys;
         a.n_triples = p->n_triples; a.nbins = p->nbins;
-        long long total = (long long)nf * b.n_atoms;
+        long long total = (long long)nf * b.n_keep;
         if (total > 0) {
-            k_bad<<<(unsigned)((total + 127) / 128), 128, 0, ctx->s_compute>>>(a);   // blocks beyond the centre count return at once
+            k_bad<<<(unsigned)((total + 127) / 128), 128, 0, ctx->s_compute>>>(a);   // one thread per atom of the filtered, cell-sorted frames
             ctx->launches += 1;
             CUDA_TRY(ctx, cudaGetLastError());
         }

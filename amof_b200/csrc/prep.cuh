@@ -34,10 +34,9 @@ struct PrepArgs {
     SAtom *sorted;            // [F*N]
     int n_atoms;
     int n_frames;
-    // optional compaction of "centre" atoms (bond angles): species_flag[s] != 0 -> append the sorted index
-    const uint8_t *species_flag;   // [n_species] or nullptr
-    uint32_t *centres;             // [F*N]
-    int *n_centres;
+    // optional filter (bond angles): only atoms with species_keep[species] != 0 enter the cell list; the others can
+    // neither be a centre nor a neighbour under the cutoff matrix, so the sorted frame holds cell_start[ncell] atoms
+    const uint8_t *species_keep;   // [n_species] or nullptr
 };
 
 __device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__restrict__ p, double *pw, int *c) {
@@ -65,6 +64,7 @@ __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         int f = (int)(idx / a.n_atoms);
+        if (a.species_keep && !a.species_keep[a.species[idx - (long long)f * a.n_atoms]]) { a.cid[idx] = 0xffffffffu; continue; }
         const FrameGeom &g = a.geom[f];
         double pw[3];
         int c[3];
@@ -76,58 +76,67 @@ __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
 }
 
 // one block per frame; writes ncell+1 entries (last = number of atoms).  Each thread scans SCAN_PER consecutive
-// cells serially, the block scans the per-thread totals: ncell / (1024 * SCAN_PER) rounds of three barriers.
+// cells serially, every warp publishes its total, and after ONE barrier per round each warp scans the 32 warp totals
+// itself (redundantly), so the running carry lives in a register of every thread: no second barrier, no shared carry.
 #define SCAN_PER 8
 __global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
+    __shared__ uint32_t warp_sums[2][32];      // double-buffered: round r+1 may publish while a slow warp still reads round r
     int f = blockIdx.x;
     const FrameGeom &g = a.geom[f];
     const uint32_t *cnt = a.cell_count + g.cs_off;
     uint32_t *out = a.cell_start + g.cs_off;
     int n = g.ncell;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x * SCAN_PER) {
+    const int nwarp = blockDim.x >> 5;
+    uint32_t carry = 0;
+    int buf = 0;
+    for (int base = 0; base < n; base += blockDim.x * SCAN_PER, buf ^= 1) {
         const int i0 = base + threadIdx.x * SCAN_PER;
         uint32_t loc[SCAN_PER];
         uint32_t v = 0;
+        if (i0 + SCAN_PER <= n && (reinterpret_cast<uintptr_t>(cnt + i0) & 15) == 0) {
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(cnt + i0), q1 = *reinterpret_cast<const uint4 *>(cnt + i0 + 4);
+            loc[0] = q0.x; loc[1] = q0.y; loc[2] = q0.z; loc[3] = q0.w; loc[4] = q1.x; loc[5] = q1.y; loc[6] = q1.z; loc[7] = q1.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < SCAN_PER; ++k) {
-            loc[k] = (i0 + k < n) ? cnt[i0 + k] : 0u;
-            v += loc[k];
+            for (int k = 0; k < SCAN_PER; ++k) loc[k] = (i0 + k < n) ? cnt[i0 + k] : 0u;
         }
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; ++k) v += loc[k];
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) warp_sums[warp] = incl;
+        if (lane == 31) warp_sums[buf][warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t ws = warp_sums[lane];
-            uint32_t wi = ws;
+        const uint32_t ws = lane < nwarp ? warp_sums[buf][lane] : 0u;
+        uint32_t wi = ws;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        const uint32_t before = __shfl_sync(0xffffffffu, wi - ws, warp);      // total of the warps before mine
+        const uint32_t round_total = __shfl_sync(0xffffffffu, wi, 31);
+        uint32_t run = carry + before + incl - v;
+        if (i0 + SCAN_PER <= n && (reinterpret_cast<uintptr_t>(out + i0) & 15) == 0) {
+            uint4 q0, q1;
+            q0.x = run; run += loc[0]; q0.y = run; run += loc[1]; q0.z = run; run += loc[2]; q0.w = run; run += loc[3];
+            q1.x = run; run += loc[4]; q1.y = run; run += loc[5]; q1.z = run; run += loc[6]; q1.w = run;
+            *reinterpret_cast<uint4 *>(out + i0) = q0;
+            *reinterpret_cast<uint4 *>(out + i0 + 4) = q1;
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; ++k) {
+                if (i0 + k < n) out[i0 + k] = run;
+                run += loc[k];
             }
-            warp_sums[lane] = wi - ws;   // exclusive prefix of the warp totals
         }
-        __syncthreads();
-        uint32_t run = carry_s + warp_sums[warp] + incl - v;
-#pragma unroll
-        for (int k = 0; k < SCAN_PER; ++k) {
-            if (i0 + k < n) out[i0 + k] = run;
-            run += loc[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = run;
-        __syncthreads();
+        carry += round_total;
     }
-    if (threadIdx.x == 0) out[n] = carry_s;
+    if (threadIdx.x == 0) out[n] = carry;
 }
 
 __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
          idx += (long long)gridDim.x * blockDim.x) {
         int f = (int)(idx / a.n_atoms);
         int i = (int)(idx - (long long)f * a.n_atoms);
+        if (a.cid[idx] == 0xffffffffu) continue;          // filtered out by species_keep
         const FrameGeom &g = a.geom[f];
         double pw[3];
         int c[3];
@@ -146,18 +156,5 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         // species | c0 << 8 | c1 << 20 | c2 << 32   (nc <= 1024 per axis)
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
-        if (a.species_flag) {
-            // warp-aggregated append: one atomic per warp on the single list counter instead of one per centre
-            const bool is_centre = a.species_flag[a.species[i]] != 0;
-            const unsigned active = __activemask();
-            const unsigned m = __ballot_sync(active, is_centre);
-            if (m) {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(a.n_centres, __popc(m));
-                base = __shfl_sync(active, base, leader);
-                if (is_centre) a.centres[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)((long long)f * a.n_atoms + dst);
-            }
-        }
     }
 }

@@ -22,7 +22,7 @@ def _walk(seed, T, n, tri=True, size=12.0, step=0.4, wrapped=True, nspec=3):
     return pos, cells, spec, masses
 
 
-def _gpu_window(backend, pos, cells, spec, masses, S, window, unwrap):
+def _gpu_window(backend, pos, cells, spec, masses, S, window, unwrap, raw_sums=False):
     T = len(pos)
     with backend.msd_open(T, masses, spec, S, cells) as s:
         s.load(0, pos[:T // 2])
@@ -35,6 +35,8 @@ def _gpu_window(backend, pos, cells, spec, masses, S, window, unwrap):
         com = sums[:, :3] / sums[:, 3:4]
         s.set_com(com)
         raw = s.window(np.asarray(window, dtype=np.int32))
+    if raw_sums:
+        return raw, com, new_pos
     n_of = np.bincount(spec, minlength=S).astype(np.float64)
     msd = raw / n_of[:, None] / (T - np.asarray(window, dtype=np.float64))[None, :]
     return msd, com, new_pos
@@ -59,6 +61,43 @@ def test_window_msd(backend, seed, T, n, tri, unwrap):
     if unwrap:
         # oracle returns unwrapped AND com-shifted positions; undo the shift with the GPU's own com
         np.testing.assert_allclose(new_pos - com[:, None, :], mutated, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("T,delta,env", [
+    (200, 1, {}),                                                  # 100 window lengths: several groups and passes
+    (203, 7, {}),                                                  # remainder frames after the last full super-row
+    (161, 5, {"AMOFB_MSD_AP_NWT": "5", "AMOFB_MSD_AP_NG": "2", "AMOFB_MSD_AP_WPG": "3"}),   # 16 windows in 2 passes of 2 x 5
+    (161, 5, {"AMOFB_MSD_AP_NWT": "13", "AMOFB_MSD_AP_NG": "1", "AMOFB_MSD_AP_WPG": "16"}),
+    (161, 5, {"AMOFB_MSD_AP_NWT": "9", "AMOFB_MSD_AP_NG": "4", "AMOFB_MSD_AP_WPG": "1"}),   # a group with no requested window in pass 1
+    (120, 10, {"AMOFB_MSD_NO_AP": "1"}),                           # generic kernel on the same kind of request
+])
+def test_window_msd_arithmetic_progression(backend, monkeypatch, T, delta, env):
+    """WindowMsd's own request (window = arange(0, T//2, delta), msd.py:176-178) through every launch shape of the
+    register-tiled kernel, against the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    S = 3
+    pos, cells, spec, masses = _walk(40 + T + delta, T, 37, True)
+    window = np.arange(0, T // 2, delta)
+    got, _, _ = _gpu_window(backend, pos, cells, spec, masses, S, window, False)
+    want, _ = orc.msd_window(pos, cells, masses, spec, S, window)
+    assert np.all(got[:, 0] == 0.0)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-13)
+
+
+def test_window_msd_irregular_windows(backend):
+    """window lengths that are NOT an arithmetic progression (only reachable through the C ABI) -> generic kernel;
+    lengths >= T contribute nothing"""
+    S = 3
+    pos, cells, spec, masses = _walk(77, 90, 41, True)
+    window = np.array([0, 2, 5, 11, 12, 40, 89, 90, 500])
+    raw, _, _ = _gpu_window(backend, pos, cells, spec, masses, S, window, False, raw_sums=True)
+    ok = window < 90
+    want, _ = orc.msd_window(pos, cells, masses, spec, S, window[ok])
+    n_of = np.bincount(spec, minlength=S).astype(np.float64)
+    got = raw[:, ok] / n_of[:, None] / (90 - window[ok].astype(np.float64))[None, :]
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-13)
+    assert np.all(raw[:, ~ok] == 0.0)
 
 
 def test_msd_get_positions_roundtrip(backend):
