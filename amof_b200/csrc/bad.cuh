@@ -43,7 +43,10 @@ __device__ __forceinline__ int bad_bin(double t, const double *__restrict__ tthr
 // One THREAD per atom of the cell-sorted frame, in sorted order: the cell list only holds the species that appear in
 // the cutoff matrix (PrepArgs::species_keep), so nearly every thread is a centre, and neighbouring threads sit in the
 // same or adjacent cells -- their cell_start[] and candidate reads hit the same lines.
-__global__ void __launch_bounds__(128) k_bad(BadArgs a) {
+#ifndef BAD_MIN_BLOCKS
+#define BAD_MIN_BLOCKS 8      // 64 registers: measured best on C4 (tools/sweep_bad.sh)
+#endif
+__global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad(BadArgs a) {
     const long long t_id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t_id >= (long long)a.n_frames * a.n_keep) return;
     const int f = (int)(t_id / a.n_keep);
@@ -64,31 +67,42 @@ __global__ void __launch_bounds__(128) k_bad(BadArgs a) {
     unsigned char sp[BAD_NB_MAX];
     int nn = 0;
     bool overflow = false;
+    const double mex = me.x, mey = me.y, mez = me.z;
+    const uint16_t *krow = a.keyidx + si * S;
     for (int d0 = -m0; d0 <= m0; ++d0) {
-        const int t0 = c0 + d0, s0 = floordiv_i(t0, nc0), q0 = t0 - s0 * nc0;
+        int s0, q0;
+        wrap_cell(c0 + d0, nc0, s0, q0);
         for (int d1 = -m1; d1 <= m1; ++d1) {
-            const int t1 = c1 + d1, s1 = floordiv_i(t1, nc1), q1 = t1 - s1 * nc1;
+            int s1, q1;
+            wrap_cell(c1 + d1, nc1, s1, q1);
             const int rowbase = (q0 * nc1 + q1) * nc2;
+            // P3 image shift, (s0*a + s1*b) part: zero for most rows
+            double Rx = 0.0, Ry = 0.0, Rz = 0.0;
+            if ((s0 | s1) != 0) {
+                const double fs0 = (double)s0, fs1 = (double)s1;
+                Rx = fs0 * G.cell[0] + fs1 * G.cell[3]; Ry = fs0 * G.cell[1] + fs1 * G.cell[4]; Rz = fs0 * G.cell[2] + fs1 * G.cell[5];
+            }
             int d2 = -m2;
             while (d2 <= m2) {
-                const int t2 = c2 + d2, s2 = floordiv_i(t2, nc2), q2 = t2 - s2 * nc2;
+                int s2, q2;
+                wrap_cell(c2 + d2, nc2, s2, q2);
                 const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
                 const int jb = (int)cs[rowbase + q2], je = (int)cs[rowbase + q2 + len];
-                const bool self_image = (s0 == 0 && s1 == 0 && s2 == 0);
-                const double fs0 = (double)s0, fs1 = (double)s1, fs2 = (double)s2;
-                const double Tx = (fs0 * G.cell[0] + fs1 * G.cell[3]) + fs2 * G.cell[6];
-                const double Ty = (fs0 * G.cell[1] + fs1 * G.cell[4]) + fs2 * G.cell[7];
-                const double Tz = (fs0 * G.cell[2] + fs1 * G.cell[5]) + fs2 * G.cell[8];
+                d2 += len;
+                if (je <= jb) continue;
+                const bool self_image = ((s0 | s1 | s2) == 0);
+                double Tx = Rx, Ty = Ry, Tz = Rz;          // (0 + 0) + s2*c == s2*c and x + 0.0 == x: same bits as the full P3 sum
+                if (s2 != 0) { const double fs2 = (double)s2; Tx = Rx + fs2 * G.cell[6]; Ty = Ry + fs2 * G.cell[7]; Tz = Rz + fs2 * G.cell[8]; }
                 for (int j = jb; j < je; ++j) {
                     if (self_image && j == i) continue;
                     const SAtom o = load_satom(fr + j);
-                    const double dx = (o.x - me.x) + Tx;
-                    const double dy = (o.y - me.y) + Ty;
-                    const double dz = (o.z - me.z) + Tz;
+                    const double dx = (o.x - mex) + Tx;
+                    const double dy = (o.y - mey) + Ty;
+                    const double dz = (o.z - mez) + Tz;
                     const double dd = (dx * dx + dy * dy) + dz * dz;
                     if (dd < a.r2search) {
                         const int sj = (int)(o.s & 0xff);
-                        if (dd < __ldg(a.cn_thr2 + a.keyidx[si * S + sj])) {
+                        if (dd < __ldg(a.cn_thr2 + krow[sj])) {
                             if (nn < BAD_NB_MAX) {
                                 const double n = sqrt(dd);          // P6: u = v / |v|, componentwise
                                 ux[nn] = dx / n; uy[nn] = dy / n; uz[nn] = dz / n;
@@ -98,7 +112,6 @@ __global__ void __launch_bounds__(128) k_bad(BadArgs a) {
                         }
                     }
                 }
-                d2 += len;
             }
         }
     }

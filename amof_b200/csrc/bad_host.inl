@@ -112,7 +112,11 @@ extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const
         }
     p->r2search = 0.0;
     for (double t : cnthr) p->r2search = std::max(p->r2search, t);
-    host_angle_thresholds(dtheta, nbins, tthr);
+    if (ctx->tthr_nbins == nbins && ctx->tthr_dtheta == dtheta && (int)ctx->tthr_cache.size() == nbins + 2) tthr = ctx->tthr_cache;
+    else {
+        host_angle_thresholds(dtheta, nbins, tthr);
+        ctx->tthr_cache = tthr; ctx->tthr_dtheta = dtheta; ctx->tthr_nbins = nbins;
+    }
     std::vector<uint16_t> keyidx((size_t)S * S);
     for (int a = 0; a < S; ++a)
         for (int b = 0; b < S; ++b) keyidx[a * S + b] = (uint16_t)fold_key(a, b, S);

@@ -39,6 +39,11 @@ struct amofb_ctx {
     double edge_rmax = 0.0;
     int edge_nbins = 0;
     std::vector<double> edge_cache;
+    // last bond-angle threshold table (3 600 bisections through libm acos: a few ms, identical for every analysis with
+    // the same dtheta / bin count)
+    double tthr_dtheta = 0.0;
+    int tthr_nbins = 0;
+    std::vector<double> tthr_cache;
     std::vector<PoolBlock> pool_idle;
     std::unordered_map<void *, PoolBlock> pool_live;
     cudaStream_t s_compute = nullptr;

@@ -360,14 +360,19 @@ __device__ __forceinline__ void msd_ap_tile(const double *__restrict__ sm, int t
 }
 
 // ng groups of NWT windows per pass (ng * NWT windows; those beyond nw are formed and dropped); blockDim.x = 32 * ng * (warps per group)
-template <int KB, int NWT>
+// prepare != 0: P still holds the positions; the centre-of-mass shift, the displacement wrap (P8) and the running sum
+// along time that k_msd_scan<PREPARE> would write back to HBM are done here, on the staged series, every time an atom
+// is loaded: one 24*N*T read instead of a read, a write and another read.
+template <int KB, int NWT, bool FIXED_CELL>
 __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *__restrict__ P, const uint8_t *__restrict__ species, int n, int T,
-                                                                  int delta, int nw, int ng, int S, double *__restrict__ partial) {
+                                                                  int delta, int nw, int ng, int S, double *__restrict__ partial,
+                                                                  const MsdGeom *__restrict__ geom, const double *__restrict__ com, int prepare) {
     constexpr int nwt = NWT;
     extern __shared__ double sm[];
     const int tp = (T + 1) & ~1;                            // padded series length (keeps y[] and z[] 16-byte aligned)
     double *s_acc = sm + 3 * (size_t)tp;                    // [S][nw] block accumulators (after the staged series)
     double *s_red = s_acc + (size_t)S * nw;                 // [nwarp][NWT]
+    double *s_scan = s_red + (size_t)MSD_NW * (MSD_AP_THREADS / 32);   // [32][3] warp totals of the in-block running sum
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int grp = warp % ng, wpg = nwarp / ng;            // my window group; warps per group
     const int tg = (warp / ng) * 32 + lane, gs = wpg * 32;  // my index among the group's threads
@@ -446,6 +451,48 @@ __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + ((size_t)i << 7)));
             }
             __syncthreads();
+            if (prepare) {
+                // thread t owns the frames [t*C, t*C + C), C odd (conflict-free 8-byte strides): wrap + local running sum in
+                // place, then one block-wide exclusive scan of the per-thread totals.  (Measured: forming the displacements
+                // in parallel over frames first, with coalesced centre-of-mass reads, is 8 % slower on C5.)
+                const int C = ((T + (int)blockDim.x - 1) / (int)blockDim.x) | 1;
+                const int k0 = threadIdx.x * C, k1 = min(T, k0 + C);
+                double px = 0.0, py = 0.0, pz = 0.0;        // shifted position of the frame before my first one
+                if (k0 >= 1 && k0 < T) {
+                    px = sm[k0 - 1] - com[3 * (size_t)(k0 - 1)];
+                    py = sm[tp + k0 - 1] - com[3 * (size_t)(k0 - 1) + 1];
+                    pz = sm[2 * tp + k0 - 1] - com[3 * (size_t)(k0 - 1) + 2];
+                }
+                __syncthreads();                            // every predecessor is read before anybody overwrites it
+                double sx = 0.0, sy = 0.0, sz = 0.0;
+                {
+                    MsdGeom g0;
+                    if (FIXED_CELL) g0 = geom[0];
+                    for (int k = k0; k < k1; ++k) {
+                        const double x = sm[k] - com[3 * (size_t)k], y = sm[tp + k] - com[3 * (size_t)k + 1], z = sm[2 * tp + k] - com[3 * (size_t)k + 2];
+                        double dx, dy, dz;
+                        if (k == 0) { dx = x; dy = y; dz = z; }                                     // delta_0 = first positions
+                        else wrap_disp(FIXED_CELL ? g0 : geom[k - 1], x - px, y - py, z - pz, dx, dy, dz);   // cell of frame k-1 wraps k-1 -> k
+                        px = x; py = y; pz = z;
+                        sx += dx; sy += dy; sz += dz;
+                        sm[k] = sx; sm[tp + k] = sy; sm[2 * tp + k] = sz;
+                    }
+                }
+                const double ix = warp_incl_scan(sx, lane), iy = warp_incl_scan(sy, lane), iz = warp_incl_scan(sz, lane);
+                if (lane == 31) { s_scan[3 * warp] = ix; s_scan[3 * warp + 1] = iy; s_scan[3 * warp + 2] = iz; }
+                __syncthreads();
+                double ox, oy, oz;
+                {
+                    const double tx = lane < nwarp ? s_scan[3 * lane] : 0.0, ty = lane < nwarp ? s_scan[3 * lane + 1] : 0.0,
+                                 tz = lane < nwarp ? s_scan[3 * lane + 2] : 0.0;
+                    const double wx = warp_incl_scan(tx, lane), wy = warp_incl_scan(ty, lane), wz = warp_incl_scan(tz, lane);
+                    ox = __shfl_sync(0xffffffffu, wx - tx, warp) + (ix - sx);       // warps before mine + lanes before me
+                    oy = __shfl_sync(0xffffffffu, wy - ty, warp) + (iy - sy);
+                    oz = __shfl_sync(0xffffffffu, wz - tz, warp) + (iz - sz);
+                }
+                for (int k = k0; k < k1; ++k) { sm[k] += ox; sm[tp + k] += oy; sm[2 * tp + k] += oz; }
+                __syncthreads();
+            }
             if (mine) {
                 for (int q = tg; q < ntask; q += gs) {
                     const int s = q / delta, r = q - s * delta;

@@ -194,21 +194,27 @@ extern "C" int amofb_msd_set_com(amofb_ctx *ctx, const double *com) {
     return AMOFB_OK;
 }
 
+// k_msd_scan<PREPARE>: centre-of-mass shift, displacement wrap and running sum written back over the trajectory
+static int msd_prepare(amofb_ctx *ctx, MsdState *p) {
+    if (!p->have_com) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_window needs amofb_msd_set_com first");
+    if (p->fixed_cell) k_msd_scan<true, true><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
+    else k_msd_scan<true, false><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    p->prepared = true;
+    return AMOFB_OK;
+}
+
 extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window, double *sums) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_window"));
     if (p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "positions were consumed by amofb_msd_direct");
     if (n_window < 0 || (n_window > 0 && (!window || !sums))) return amofb_fail(ctx, AMOFB_ERR_ARG, "bad window arguments");
-    if (!p->prepared) {
-        if (!p->have_com) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_window needs amofb_msd_set_com first");
-        if (p->fixed_cell) k_msd_scan<true, true><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
-        else k_msd_scan<true, false><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, p->d_com, p->n, p->T);
-        ctx->launches += 1;
-        CUDA_TRY(ctx, cudaGetLastError());
-        p->prepared = true;
-    }
-    if (n_window == 0) return AMOFB_OK;
     const int S = p->S;
+    if (n_window == 0) {                                    // nothing to sum: only bring the trajectory into the prepared state
+        if (!p->prepared) AMOFB_TRY(msd_prepare(ctx, p));
+        return AMOFB_OK;
+    }
     int threads = MSD_THREADS;
     // window lengths 0, D, 2D, ... (what WindowMsd always asks for, msd.py:176-178) -> register-tiled kernel
     int ap_delta = 0;
@@ -218,6 +224,16 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
             if ((long long)window[w] != (long long)w * ap_delta) ap_delta = 0;
         if (ap_delta && (long long)MSD_AP_KB * ap_delta >= p->T) ap_delta = 0;      // not a single full tile: nothing to gain
     }
+    // the register-tiled kernel prepares the series itself (centre-of-mass shift, wrap, running sum) while it is staged;
+    // every other path needs k_msd_scan<PREPARE> to rewrite the trajectory first
+    {
+        size_t need = sizeof(double) * (3 * (size_t)p->T + 4 + (size_t)S * n_window + (size_t)MSD_NW * (MSD_AP_THREADS / 32) + 96);
+        size_t budget0 = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;
+        if (need > budget0 || env_int("AMOFB_MSD_NO_SMEM", 0)) ap_delta = 0;
+    }
+    const bool fuse_prepare = ap_delta && !p->prepared && !env_int("AMOFB_MSD_NO_FUSE", 0);
+    if (!p->prepared && !fuse_prepare) AMOFB_TRY(msd_prepare(ctx, p));
+    if (fuse_prepare && !p->have_com) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_window needs amofb_msd_set_com first");
     int ap_ng = 1, ap_nwt = 1;
     const int force_ng = env_int("AMOFB_MSD_AP_NG", 0), force_wpg = env_int("AMOFB_MSD_AP_WPG", 0), force_nwt = env_int("AMOFB_MSD_AP_NWT", 0);
     if (ap_delta) {
@@ -252,22 +268,23 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     const int nwarp = threads / 32;
     int *d_window = nullptr;
     double *d_partial = nullptr;
-    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)MSD_NW * (size_t)std::max(MSD_AP_THREADS / 32, nwarp));
+    size_t extra = sizeof(double) * ((size_t)S * n_window + (size_t)MSD_NW * (size_t)std::max(MSD_AP_THREADS / 32, nwarp) + 96);
     size_t smem_full = sizeof(double) * (3 * (size_t)p->T + 4) + extra;
     size_t budget = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;
     bool use_smem = smem_full <= budget && !env_int("AMOFB_MSD_NO_SMEM", 0);
-    if (!use_smem) ap_delta = 0;
+    if (!use_smem && ap_delta) return amofb_fail(ctx, AMOFB_ERR_STATE, "internal: shared-memory budget of the tiled window kernel");
     size_t smem = use_smem ? smem_full : extra;
     if (extra > budget) return amofb_fail(ctx, AMOFB_ERR_ARG, "too many window lengths (%d) for one pass", n_window);
     int per_sm = 1;
     const void *ap_kernel = nullptr;
     if (ap_delta) {
+        const bool fc = p->fixed_cell;
         switch (ap_nwt) {
-            case 5: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 5>; break;
-            case 7: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 7>; break;
-            case 9: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 9>; break;
-            case 11: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 11>; break;
-            default: ap_kernel = (const void *)k_msd_window_ap<MSD_AP_KB, 13>; ap_nwt = 13; break;
+            case 5: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 5, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 5, false>; break;
+            case 7: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 7, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 7, false>; break;
+            case 9: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 9, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 9, false>; break;
+            case 11: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 11, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 11, false>; break;
+            default: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 13, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 13, false>; ap_nwt = 13; break;
         }
         CUDA_TRY(ctx, cudaFuncSetAttribute(ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ap_kernel, threads, smem));
@@ -289,7 +306,10 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
         if (ap_delta) {
             const double *a_P = p->d_P; const uint8_t *a_sp = p->d_species;
             int a_n = p->n, a_T = p->T, a_S = S;
-            void *kargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_n, (void *)&a_T, (void *)&ap_delta, (void *)&n_window, (void *)&ap_ng, (void *)&a_S, (void *)&d_partial};
+            const MsdGeom *a_geom = p->d_geom; const double *a_com = p->d_com;
+            int a_prep = fuse_prepare ? 1 : 0;
+            void *kargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_n, (void *)&a_T, (void *)&ap_delta, (void *)&n_window, (void *)&ap_ng, (void *)&a_S, (void *)&d_partial,
+                             (void *)&a_geom, (void *)&a_com, (void *)&a_prep};
             e = cudaLaunchKernel(ap_kernel, dim3(grid), dim3(threads), kargs, smem, ctx->s_compute);
         } else if (use_smem) k_msd_window<true><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);
         else k_msd_window<false><<<grid, threads, smem, ctx->s_compute>>>(p->d_P, p->d_species, p->n, p->T, d_window, n_window, S, d_partial);

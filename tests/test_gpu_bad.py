@@ -65,6 +65,29 @@ def test_random_boxes(backend, seed, n, tri, size, dtheta):
     assert nf == T
 
 
+@pytest.mark.parametrize("tri", [False, True])
+def test_species_without_cutoffs_are_filtered(backend, tri):
+    """Species that appear in no cutoff pair never enter the cell list (PrepArgs::species_keep): the counts of the
+    listed triples, of 'any neighbour' (B = -1) and of 'any centre' (A = -1) triples must not change."""
+    S = 5
+    T = 3
+    frames = [random_box(70 + f, 800, S, tri, 17.0, scale_pos=2.0) for f in range(T)]
+    spec = frames[0][2]
+    pos = np.array([f[0] for f in frames])
+    cell = np.array([f[1] for f in frames])
+    cut = np.zeros((S, S))
+    cut[1, 3] = cut[3, 1] = 3.1          # species 0, 2 and 4 have no cutoff at all: 60 % of the atoms drop out
+    cut[3, 3] = 2.7
+    triples = [(1, 3), (3, 1), (3, 3), (3, -1), (-1, 3), (-1, -1), (0, 2), (2, -1)]
+    nbins = int(180 // 0.5) + 1
+    hist, dropped, nf = backend.bad_counts(spec, S, [(pos, cell)], cut, triples, 0.5, nbins)
+    want, wdrop = _oracle(pos, cell, spec, S, cut, triples, 0.5, nbins)
+    assert int(want[:6].sum()) > 100 and int(want[6:].sum()) == 0
+    assert np.array_equal(hist, want)
+    assert np.array_equal(dropped, wdrop)
+    assert nf == T
+
+
 def test_collinear_and_degenerate_angles(backend):
     """0 and 180 degree angles sit exactly on histogram edges; a short dtheta grid must agree with the oracle."""
     cell = np.diag([20.0, 20.0, 20.0])
