@@ -65,6 +65,8 @@ SIGNATURES = {
     "amofb_bad_push": (C.c_int, [_vp, C.c_int, _vp, _dp]),
     "amofb_bad_push_device": (C.c_int, [_vp, C.c_int, _vp, _dp]),
     "amofb_bad_finish": (C.c_int, [_vp, _u64p, _u64p, _i64p]),
+    "amofb_neigh_count": (C.c_int, [_vp, C.c_int, C.c_int, _u8p, _dp, _dp, _dp, _i64p]),
+    "amofb_neigh_fill": (C.c_int, [_vp, C.POINTER(C.c_int32), C.c_int64]),
     "amofb_msd_begin": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _u8p, C.c_int, _dp]),
     "amofb_msd_load": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "amofb_msd_load_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -291,6 +293,23 @@ class GpuBackend:
         nf = C.c_int64(0)
         ctx.check(lib.amofb_bad_finish(ctx.h, _ptr(hist, _u64p), _ptr(dropped, _u64p), C.byref(nf)))
         return hist, dropped, int(nf.value)
+
+    # -- explicit neighbour list --------------------------------------------------------------------
+    def neighbour_list(self, species, n_species, positions, cell, cutoff):
+        """One frame -> (offsets int64[n+1], neighbours int32[offsets[n]]): row i = neighbours[offsets[i]:offsets[i+1]],
+        ascending original indices, one entry per periodic image under cutoff[Zi][Zj] (amof/atom.py:72-87)."""
+        ctx, lib = self.ctx, self.ctx.lib
+        species = np.ascontiguousarray(species, dtype=np.uint8)
+        S = int(n_species)
+        cut = _f64(cutoff).reshape(S, S)
+        pos = _f64(positions).reshape(len(species), 3)
+        cell = _f64(cell).reshape(3, 3)
+        offsets = np.zeros(len(species) + 1, dtype=np.int64)
+        ctx.check(lib.amofb_neigh_count(ctx.h, len(species), S, _ptr(species, _u8p), _ptr(cut, _dp), _ptr(pos, _dp),
+                                        _ptr(cell, _dp), _ptr(offsets, _i64p)))
+        nbr = np.zeros(int(offsets[-1]), dtype=np.int32)
+        ctx.check(lib.amofb_neigh_fill(ctx.h, _ptr(nbr, C.POINTER(C.c_int32)) if len(nbr) else None, len(nbr)))
+        return offsets, nbr
 
     # -- MSD --------------------------------------------------------------------------------------
     def msd_open(self, n_frames, masses, species, n_species, cells):

@@ -1,8 +1,9 @@
 """
 Helpers on single frames, same names and meaning as /root/reference/amof/atom.py.
 
-``get_neighborlist`` is deliberately NOT provided as a Python list-of-lists (atom.py:72-87): on the GPU path the
-neighbour search is fused with the counting (amof_b200.cn) and the angle enumeration (amof_b200.bad).
+The analyses (amof_b200.cn, amof_b200.bad) never build a neighbour list: the search is fused with the counting and
+the angle enumeration on the device.  ``get_neighborlist`` is kept for the callers that want the list itself
+(amof.ring, amof.coordination) and runs the same GPU search through ``amofb_neigh_count`` / ``amofb_neigh_fill``.
 """
 import numpy as np
 
@@ -46,6 +47,28 @@ def format_cutoff(nb_set_and_cutoff, format='ase', sort_pair=False):
                 xx = tuple(sorted(xx))
             cutoff_dict[xx] = cutoff
         return cutoff_dict
+
+
+def get_neighborlist_csr(atom, cutoff_dict, backend=None):
+    """Neighbour list of one frame in CSR form: ``(offsets int64[n+1], neighbours int32[offsets[n]])``.
+
+    Same pairs as ``ase.neighborlist.neighbor_list('ij', atom, cutoff_dict)`` (amof/atom.py:82): j is a neighbour of
+    i iff d < cutoff[(Zi, Zj)] (both key orders, unlisted pairs never), once per periodic image, without the
+    zero-shift self pair.  Inside a row the indices are ascending (ase leaves that order unspecified)."""
+    from . import _lib, frames
+    backend = backend or _lib.get_backend()
+    numbers = np.asarray(atom.get_atomic_numbers())
+    zs, spec = frames.species_index(numbers)
+    cut = cutoff_matrix(cutoff_dict, zs)
+    return backend.neighbour_list(spec, len(zs), atom.get_positions(), np.asarray(atom.get_cell(), dtype=np.float64), cut)
+
+
+def get_neighborlist(atom, cutoff_dict, backend=None):
+    """list (one entry per atom) of lists of neighbour indices, as amof.atom.get_neighborlist (atom.py:72-87)"""
+    offsets, nbr = get_neighborlist_csr(atom, cutoff_dict, backend)
+    flat = nbr.tolist()
+    off = offsets.tolist()
+    return [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
 def cutoff_matrix(cutoff_dict, zs):

@@ -6,6 +6,7 @@
 #include "pair_tiled.cuh"
 #include "pair_warp.cuh"
 #include "pair_pipe.cuh"
+#include "neigh.cuh"
 #include "bad.cuh"
 #include "msd.cuh"
 
@@ -49,6 +50,7 @@ extern "C" int amofb_create(int device, amofb_ctx **out) {
 static void pair_release(amofb_ctx *ctx);
 static void bad_release(amofb_ctx *ctx);
 static void msd_release(amofb_ctx *ctx);
+static void neigh_release(amofb_ctx *ctx);
 static void pool_destroy(amofb_ctx *ctx);
 
 extern "C" int amofb_destroy(amofb_ctx *ctx) {
@@ -58,6 +60,7 @@ extern "C" int amofb_destroy(amofb_ctx *ctx) {
     pair_release(ctx);
     bad_release(ctx);
     msd_release(ctx);
+    neigh_release(ctx);
     for (auto &p : ctx->pending_pair_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto &t : ctx->timer) if (t) cudaEventDestroy(t);
     pool_destroy(ctx);
@@ -254,6 +257,7 @@ struct BatchSlot {
     FrameGeom *d_geom = nullptr, *h_geom = nullptr;
     uint32_t *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cid = nullptr, *d_rank = nullptr;
     SAtom *d_sorted = nullptr;
+    uint32_t *d_orig = nullptr;            // only when the batcher was asked for it (want_orig)
     unsigned long long *d_out = nullptr, *h_out = nullptr;   // per-frame outputs of the batch
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     int frames = 0;        // frames of the batch in flight (0 = idle)
@@ -268,6 +272,7 @@ struct Batcher {
     uint8_t *d_species = nullptr;
     uint8_t *d_species_keep = nullptr;   // optional species filter of the cell list (bond angles)
     int n_keep = 0;                      // atoms per frame that pass it (= n_atoms without a filter)
+    bool want_orig = false;              // keep the original index of every sorted atom
     BatchSlot slot[2];
     int next = 0;
     int64_t frames_seen = 0;
@@ -279,7 +284,7 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
     for (auto &s : b.slot) {
         pool_put(ctx, s.d_raw); pool_put(ctx, s.d_geom); pool_put(ctx, s.h_geom);
         pool_put(ctx, s.d_cell_count); pool_put(ctx, s.d_cell_start); pool_put(ctx, s.d_cid); pool_put(ctx, s.d_rank);
-        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
+        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
@@ -289,7 +294,7 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
 }
 
 static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *species, double rcut, int cell_div,
-                        int per_frame_out) {
+                        int per_frame_out, int max_frames = 0) {
     b.n_atoms = n_atoms;
     b.n_keep = n_atoms;
     b.rcut = rcut;
@@ -298,6 +303,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
     long long target = env_int("AMOFB_BATCH_ATOMS", 1 << 22);     // 4 Mi atoms per batch: measured +22 % (BAD), +3 % (RDF) over 1 Mi
     long long cap = target / std::max(n_atoms, 1);
     b.cap_frames = (int)std::min<long long>(std::max<long long>(cap, 1), 8192);
+    if (max_frames > 0 && b.cap_frames > max_frames) b.cap_frames = max_frames;
     b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0) + 1;
     AMOFB_TRY(dev_alloc(ctx, &b.d_species, (size_t)n_atoms));
     CUDA_TRY(ctx, cudaMemcpy(b.d_species, species, (size_t)n_atoms, cudaMemcpyHostToDevice));
@@ -311,6 +317,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
         AMOFB_TRY(dev_alloc(ctx, &s.d_cid, na));
         AMOFB_TRY(dev_alloc(ctx, &s.d_rank, na));
         AMOFB_TRY(dev_alloc(ctx, &s.d_sorted, na));
+        if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_orig, na));
         if (per_frame_out > 0) {
             AMOFB_TRY(dev_alloc(ctx, &s.d_out, (size_t)b.cap_frames * per_frame_out));
             AMOFB_TRY(pinned_alloc(ctx, &s.h_out, (size_t)b.cap_frames * per_frame_out));
@@ -370,6 +377,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.cell_count = s.d_cell_count; pa.cell_start = s.d_cell_start; pa.cid = s.d_cid; pa.rank = s.d_rank;
     pa.sorted = s.d_sorted; pa.n_atoms = b.n_atoms; pa.n_frames = nf;
     pa.species_keep = b.d_species_keep;
+    pa.orig = s.d_orig;
     long long total = (long long)nf * b.n_atoms;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;
@@ -904,3 +912,4 @@ extern "C" int amofb_cn_finish(amofb_ctx *ctx, uint64_t *cn_counts, int64_t cn_f
 
 #include "bad_host.inl"
 #include "msd_host.inl"
+#include "neigh_host.inl"

@@ -24,6 +24,7 @@
 struct PairState;
 struct BadState;
 struct MsdState;
+struct NeighState;
 
 // Buffers released by an analysis are kept by the context and handed to the next one: begin/finish pairs run once
 // per trajectory pass, and cudaMalloc / cudaHostAlloc / cudaFree each cost more than a whole batch of kernels.
@@ -60,6 +61,7 @@ struct amofb_ctx {
     PairState *pair = nullptr;
     BadState *bad = nullptr;
     MsdState *msd = nullptr;
+    NeighState *neigh = nullptr;
 };
 
 static int amofb_fail(amofb_ctx *ctx, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));

@@ -81,6 +81,16 @@ __device__ __forceinline__ void wrap_disp(const MsdGeom &G, double dx, double dy
     oz = (g0 * G.cell[2] + g1 * G.cell[5]) + g2 * G.cell[8];
 }
 
+// The same for a cell whose six off-diagonal entries (and therefore those of its inverse, P1) are zero: every dropped
+// product is +-0 and x + (+-0) == x, so the results are those of wrap_disp bit for bit (up to the sign of a zero).
+__device__ __forceinline__ void wrap_disp_diag(double i0, double i4, double i8, double c0, double c4, double c8,
+                                               double dx, double dy, double dz, double &ox, double &oy, double &oz) {
+    const double shift = (0.0 - 0.5) - 1e-7;
+    ox = (np_mod1(dx * i0 - shift) + shift) * c0;
+    oy = (np_mod1(dy * i4 - shift) + shift) * c4;
+    oz = (np_mod1(dz * i8 - shift) + shift) * c8;
+}
+
 __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -363,7 +373,7 @@ __device__ __forceinline__ void msd_ap_tile(const double *__restrict__ sm, int t
 // prepare != 0: P still holds the positions; the centre-of-mass shift, the displacement wrap (P8) and the running sum
 // along time that k_msd_scan<PREPARE> would write back to HBM are done here, on the staged series, every time an atom
 // is loaded: one 24*N*T read instead of a read, a write and another read.
-template <int KB, int NWT, bool FIXED_CELL>
+template <int KB, int NWT, int CELL>      // CELL: 0 = one cell per frame, 1 = the same cell in every frame, 2 = the same orthorhombic cell
 __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *__restrict__ P, const uint8_t *__restrict__ species, int n, int T,
                                                                   int delta, int nw, int ng, int S, double *__restrict__ partial,
                                                                   const MsdGeom *__restrict__ geom, const double *__restrict__ com, int prepare) {
@@ -467,12 +477,15 @@ __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *
                 double sx = 0.0, sy = 0.0, sz = 0.0;
                 {
                     MsdGeom g0;
-                    if (FIXED_CELL) g0 = geom[0];
+                    if (CELL == 1) g0 = geom[0];
+                    double i0 = 0.0, i4 = 0.0, i8 = 0.0, c0 = 0.0, c4 = 0.0, c8 = 0.0;
+                    if (CELL == 2) { i0 = geom[0].inv[0]; i4 = geom[0].inv[4]; i8 = geom[0].inv[8]; c0 = geom[0].cell[0]; c4 = geom[0].cell[4]; c8 = geom[0].cell[8]; }
                     for (int k = k0; k < k1; ++k) {
                         const double x = sm[k] - com[3 * (size_t)k], y = sm[tp + k] - com[3 * (size_t)k + 1], z = sm[2 * tp + k] - com[3 * (size_t)k + 2];
                         double dx, dy, dz;
                         if (k == 0) { dx = x; dy = y; dz = z; }                                     // delta_0 = first positions
-                        else wrap_disp(FIXED_CELL ? g0 : geom[k - 1], x - px, y - py, z - pz, dx, dy, dz);   // cell of frame k-1 wraps k-1 -> k
+                        else if (CELL == 2) wrap_disp_diag(i0, i4, i8, c0, c4, c8, x - px, y - py, z - pz, dx, dy, dz);
+                        else wrap_disp(CELL == 1 ? g0 : geom[k - 1], x - px, y - py, z - pz, dx, dy, dz);   // cell of frame k-1 wraps k-1 -> k
                         px = x; py = y; pz = z;
                         sx += dx; sy += dy; sz += dz;
                         sm[k] = sx; sm[tp + k] = sy; sm[2 * tp + k] = sz;

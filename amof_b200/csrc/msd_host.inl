@@ -10,7 +10,7 @@ struct MsdState {
     double *d_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     int stage_frames = 0, next_stage = 0;
-    bool have_com = false, prepared = false, consumed = false, fixed_cell = false;
+    bool have_com = false, prepared = false, consumed = false, fixed_cell = false, diag_cell = false;
     std::vector<double> cell;         // host copy [T][9]
     double mass_sum = 0.0;
 };
@@ -57,6 +57,10 @@ extern "C" int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const 
     p->fixed_cell = true;
     for (int k = 1; k < n_frames && p->fixed_cell; ++k)
         if (memcmp(cell + 9 * (size_t)k, cell, sizeof(double) * 9) != 0) p->fixed_cell = false;
+    // orthorhombic box along the axes: the off-diagonal entries of the cell AND of its inverse are all zero
+    p->diag_cell = p->fixed_cell;
+    for (int q = 0; q < 9 && p->diag_cell; ++q)
+        if (q % 4 != 0 && (geom[0].cell[q] != 0.0 || geom[0].inv[q] != 0.0)) p->diag_cell = false;
     if ((rc = dev_alloc(ctx, &p->d_P, (size_t)n_atoms * n_frames * 3))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_geom, (size_t)n_frames))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_masses, (size_t)n_atoms))) return fail(rc);
@@ -278,14 +282,17 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     int per_sm = 1;
     const void *ap_kernel = nullptr;
     if (ap_delta) {
-        const bool fc = p->fixed_cell;
+        const int cm = p->diag_cell ? 2 : (p->fixed_cell ? 1 : 0);
+#define AMOFB_AP_KERNEL(NWT_) (cm == 2 ? (const void *)k_msd_window_ap<MSD_AP_KB, NWT_, 2> : cm == 1 ? (const void *)k_msd_window_ap<MSD_AP_KB, NWT_, 1> \
+                                        : (const void *)k_msd_window_ap<MSD_AP_KB, NWT_, 0>)
         switch (ap_nwt) {
-            case 5: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 5, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 5, false>; break;
-            case 7: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 7, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 7, false>; break;
-            case 9: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 9, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 9, false>; break;
-            case 11: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 11, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 11, false>; break;
-            default: ap_kernel = fc ? (const void *)k_msd_window_ap<MSD_AP_KB, 13, true> : (const void *)k_msd_window_ap<MSD_AP_KB, 13, false>; ap_nwt = 13; break;
+            case 5: ap_kernel = AMOFB_AP_KERNEL(5); break;
+            case 7: ap_kernel = AMOFB_AP_KERNEL(7); break;
+            case 9: ap_kernel = AMOFB_AP_KERNEL(9); break;
+            case 11: ap_kernel = AMOFB_AP_KERNEL(11); break;
+            default: ap_kernel = AMOFB_AP_KERNEL(13); ap_nwt = 13; break;
         }
+#undef AMOFB_AP_KERNEL
         CUDA_TRY(ctx, cudaFuncSetAttribute(ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ap_kernel, threads, smem));
     } else if (use_smem) {

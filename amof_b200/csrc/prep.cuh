@@ -37,6 +37,7 @@ struct PrepArgs {
     // optional filter (bond angles): only atoms with species_keep[species] != 0 enter the cell list; the others can
     // neither be a centre nor a neighbour under the cutoff matrix, so the sorted frame holds cell_start[ncell] atoms
     const uint8_t *species_keep;   // [n_species] or nullptr
+    uint32_t *orig;                // optional [F*N]: original atom index of every sorted atom (explicit neighbour lists)
 };
 
 __device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__restrict__ p, double *pw, int *c) {
@@ -156,5 +157,6 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         // species | c0 << 8 | c1 << 20 | c2 << 32   (nc <= 1024 per axis)
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
+        if (a.orig) a.orig[(long long)f * a.n_atoms + dst] = (uint32_t)i;
     }
 }

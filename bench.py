@@ -505,9 +505,10 @@ def run_msd(args, backend, rank, world):
            "config": dict(wl.describe(), parallelism="atoms x%d" % world), "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": frames_total / e2e_s, "unit": wl.unit, "h2d_bytes_per_step": int(wl.bytes_in),
                    "d2h_bytes_per_step": int(raw.nbytes + wl.T * 32), "api": "amofb_msd_* via GpuBackend.msd_open"},
-           "roofline": {"bound": "hbm", "kernel": "k_msd_frame_sums + k_msd_scan + k_msd_window", "achieved": ach, "peak": peak,
+           "roofline": {"bound": "hbm", "kernel": "k_msd_frame_sums + k_msd_window_ap (shift, wrap and running sum fused in)", "achieved": ach, "peak": peak,
                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
-                        "note": "algorithmic bytes = 24*N*T read once; the three kernels read it 3x and write it once"}}
+                        "note": "algorithmic bytes = 24*N*T read once; the centre-of-mass pass and the window pass each read it once "
+                                "(2x), nothing is written back; the window kernel itself is FP64/issue-bound (7 flop per frame pair)"}}
     u = wl.units(None)
     for k, v in u.items():
         out[k] = v

@@ -128,6 +128,23 @@ int amofb_bad_push(amofb_ctx *ctx, int n_frames, const double *pos, const double
 int amofb_bad_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell);
 int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *dropped, int64_t *n_frames_out);
 
+/* ---- explicit neighbour list of one frame -------------------------------------------------------
+ * Replaces amof.atom.get_neighborlist (/root/reference/amof/atom.py:72-87):
+ *   nl_i, nl_j = ase.neighborlist.neighbor_list('ij', atom, cutoff_dict), regrouped as one list of j per atom i.
+ * The analyses above never build the list (the search is fused with the counting and with the angle enumeration);
+ * this pair of calls serves the callers that need the list itself (amof.ring, amof.coordination: SURVEY.md 8(f)).
+ * A pair (i, j, image) is listed iff d < cutoff[Zi][Zj] (strict, 0 = pair not listed); the zero-shift self pair is
+ * skipped; j appears once per periodic image under the cutoff, as ase lists it.
+ *
+ * count : one frame (pos double[n_atoms][3], cell double[9]); offsets int64[n_atoms + 1] receives the row starts
+ *         (offsets[n_atoms] = number of directed pairs).  The search state stays open for fill.
+ * fill  : neighbors int32[capacity], capacity >= offsets[n_atoms]: row i = neighbors[offsets[i] .. offsets[i+1]),
+ *         ORIGINAL atom indices in ascending order (ase's own order inside a row is unspecified).  Ends the search.
+ */
+int amofb_neigh_count(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, const double *cutoff,
+                      const double *pos, const double *cell, int64_t *offsets);
+int amofb_neigh_fill(amofb_ctx *ctx, int32_t *neighbors, int64_t capacity);
+
 /* ---- mean-squared displacement --------------------------------------------------------------
  * Replaces WindowMsd.compute_msd / compute_msd_of_m and trajectory.get_delta_pos
  * (/root/reference/amof/msd.py:186-268, amof/trajectory.py:285-303).
@@ -147,7 +164,8 @@ int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *dropped, int64_t 
  *              The caller divides by N_species*(T-m) (quirk Q4 of SURVEY.md) after its allreduce.
  * direct     : DirectMsd.compute_species_msd (msd.py:81-105), orthogonal cells only:
  *              sums[n_species][n_frames] = sum over local atoms of |r_t - r_0|^2.
- * get_positions: copy the (unwrapped and/or COM-shifted) positions back, host double[n_frames][n_atoms][3].
+ * get_positions: copy the positions (unwrapped if unwrap was called) back, host double[n_frames][n_atoms][3].
+ *              Call it before window: window may rewrite the trajectory in place (running sums of displacements).
  */
 int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const double *masses, const uint8_t *species,
                     int n_species, const double *cell);

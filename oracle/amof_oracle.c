@@ -352,6 +352,35 @@ int orc_cn_traj(int nframes, int n, const double *pos, const double *cell, const
     return rc_all;
 }
 
+/* ------------------------------------------------------------------ explicit neighbour list (P5) */
+/* amof/atom.py:72-87: nl_i, nl_j = ase.neighborlist.neighbor_list('ij', atom, cutoff_dict).  Directed pairs (i, j),
+ * one per periodic image with sqrt(d2) < cutoff[Zi][Zj]; the first `capacity` of them are stored, *count gets the total. */
+typedef struct {
+    const uint8_t *spec; int nspec; const double *cutoff; int64_t capacity, count; int32_t *pi, *pj;
+} nl_ctx;
+
+static void nl_cb(void *vctx, int i, int j, const double *dv, double d2) {
+    (void)dv;
+    nl_ctx *c = (nl_ctx *)vctx;
+    double cut = c->cutoff[c->spec[i] * c->nspec + c->spec[j]];
+    if (cut > 0.0 && sqrt(d2) < cut) {
+        if (c->count < c->capacity) { c->pi[c->count] = i; c->pj[c->count] = j; }
+        c->count += 1;
+    }
+}
+
+int orc_neighbour_pairs(int n, const double *pos, const double *cell, const uint8_t *spec, int nspec,
+                        const double *cutoff, int method, int64_t capacity, int32_t *pi, int32_t *pj, int64_t *count) {
+    if (n < 0 || nspec < 1 || !count) return ORC_ERR_ARG;
+    *count = 0;
+    double rc = max_cutoff(cutoff, nspec);
+    if (!(rc > 0.0)) return ORC_OK;
+    nl_ctx c = {spec, nspec, cutoff, capacity, 0, pi, pj};
+    int r = visit_pairs(method, n, pos, cell, rc, nl_cb, &c);
+    *count = c.count;
+    return r;
+}
+
 /* ------------------------------------------------------------------ BAD (P6, P7) */
 #define ORC_MAX_NB 64
 typedef struct {

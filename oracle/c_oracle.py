@@ -33,6 +33,8 @@ def lib():
                                    C.c_int, _u64p, _dp]
         L.orc_cn_frame.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, _u64p]
         L.orc_cn_traj.argtypes = [C.c_int, C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, _u64p]
+        L.orc_neighbour_pairs.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int64, C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.orc_bad_frame.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.c_int, C.c_int, _u64p, _u64p]
         L.orc_bad_angles.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_long]
@@ -100,6 +102,25 @@ def cn_traj(pos, cell, spec, nspec, cutoff, method=1, threads=1):
     _check(lib().orc_cn_traj(T, n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, int(threads),
                              counts.ctypes.data_as(_u64p)), "cn_traj")
     return counts
+
+
+def neighbour_pairs(pos, cell, spec, nspec, cutoff, method=1):
+    """One frame -> directed neighbour pairs (i, j) as ase.neighbor_list('ij', ...) would list them (amof/atom.py:82),
+    sorted by (i, j); a pair appears once per periodic image under the cutoff."""
+    pos, pp = _d(pos); cell, cp = _d(cell); cutoff, kp = _d(cutoff)
+    spec = np.ascontiguousarray(spec, dtype=np.uint8)
+    n = pos.shape[0]
+    count = C.c_int64(0)
+    i32p = C.POINTER(C.c_int32)
+    _check(lib().orc_neighbour_pairs(n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, 0, None, None, C.byref(count)),
+           "neighbour_pairs")
+    pi = np.zeros(count.value, dtype=np.int32)
+    pj = np.zeros(count.value, dtype=np.int32)
+    if count.value:
+        _check(lib().orc_neighbour_pairs(n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, count.value,
+                                         pi.ctypes.data_as(i32p), pj.ctypes.data_as(i32p), C.byref(count)), "neighbour_pairs")
+    order = np.lexsort((pj, pi))
+    return pi[order], pj[order]
 
 
 def bad_hist(pos, cell, spec, nspec, cutoff, A, B, dtheta, nbins, max_cn=32, method=1, hist=None):

@@ -85,6 +85,24 @@ def test_window_msd_arithmetic_progression(backend, monkeypatch, T, delta, env):
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-13)
 
 
+@pytest.mark.parametrize("tri,unwrap", [(False, False), (False, True), (True, False)])
+def test_window_msd_fixed_cell(backend, tri, unwrap):
+    """NVT trajectories: one cell for every frame (geometry kept in registers) and, for an orthorhombic box along the
+    axes, the diagonal form of the wrap -- same numbers as the general P8 arithmetic of the oracle."""
+    S = 3
+    T = 150
+    pos, cells, spec, masses = _walk(300 + int(tri), T, 53, tri, wrapped=True)
+    cells[:] = cells[0]
+    f = np.einsum('kni,ij->knj', pos, np.linalg.inv(cells[0]))
+    pos = np.einsum('kni,ij->knj', f - np.floor(f), cells[0])
+    window = np.arange(0, T // 2, 4)
+    got, com, new_pos = _gpu_window(backend, pos, cells, spec, masses, S, window, unwrap)
+    want, mutated = orc.msd_window(pos, cells, masses, spec, S, window, unwrap=unwrap)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-13)
+    if unwrap:
+        np.testing.assert_allclose(new_pos - com[:, None, :], mutated, rtol=0, atol=1e-9)
+
+
 def test_window_msd_irregular_windows(backend):
     """window lengths that are NOT an arithmetic progression (only reachable through the C ABI) -> generic kernel;
     lengths >= T contribute nothing"""

@@ -55,6 +55,46 @@ def test_zif4_cn_golden(zif4, method):
     assert 64 / 16 == 4.0 and 64 / 64 == 1.0 and abs(128 / 96 - 4 / 3) < 1e-15
 
 
+@pytest.mark.parametrize("method", [0, 1])
+def test_zif4_neighbour_list_golden(zif4, method):
+    """amof.atom.get_neighborlist on the example frame: 64 Zn->N + 64 N->Zn pairs, every Zn exactly 4 N, every N one
+    Zn; C-N@1.728: 128 + 128 directed pairs; the list and the counting form agree."""
+    spec = _spec(zif4)
+    cut = np.zeros((4, 4))
+    cut[3, 2] = cut[2, 3] = 2.5
+    i, j = orc.neighbour_pairs(zif4.positions, zif4.cell, spec, 4, cut, method=method)
+    assert len(i) == 128 == 2 * GOLD["cn_directed_pairs"]["Zn-N@2.5"]
+    deg = np.bincount(i, minlength=272)
+    assert np.all(deg[spec == 3] == 4) and np.all(deg[spec == 2] == 1) and np.all(deg[spec < 2] == 0)
+    assert np.all(spec[j[spec[i] == 3]] == 2) and np.all(spec[j[spec[i] == 2]] == 3)
+    fwd = set(zip(i.tolist(), j.tolist()))
+    assert fwd == set(zip(j.tolist(), i.tolist()))             # symmetric cutoffs: (i, j) listed iff (j, i) is
+    cut = np.zeros((4, 4))
+    cut[1, 2] = cut[2, 1] = 1.728
+    i, j = orc.neighbour_pairs(zif4.positions, zif4.cell, spec, 4, cut, method=method)
+    counts = orc.cn_counts(zif4.positions, zif4.cell, spec, 4, cut, method=method)
+    assert len(i) == 256 and int(counts[1, 2]) == 128 == int((spec[i] == 1).sum())
+
+
+def test_neighbour_list_images_and_twin():
+    """one atom in a unit cube with cutoff 1.1: its 6 face images, each listed as j = 0; sqrt(2) < 1.5 adds the 12 edge
+    images; and the numpy twin lists the same pairs on random triclinic boxes (brute force and linked cells alike)"""
+    pos = np.array([[0.3, 0.4, 0.5]])
+    spec = np.zeros(1, dtype=np.uint8)
+    for c, n in ((1.1, 6), (1.5, 18), (0.9, 0)):
+        for method in (0, 1):
+            i, j = orc.neighbour_pairs(pos, np.eye(3), spec, 1, np.array([[c]]), method=method)
+            assert len(i) == n and np.all(i == 0) and np.all(j == 0)
+    cut = np.array([[2.6, 3.0, 0.0], [3.0, 0.0, 2.8], [0.0, 2.8, 2.4]])
+    for seed, n, size in ((1, 150, 9.0), (2, 30, 4.5)):
+        p, cell, sp = random_box(seed, n, 3, True, size, scale_pos=2.0)
+        i2, j2, _, _ = npo.neighbour_pairs(p, cell, sp, cut)
+        o = np.lexsort((j2, i2))
+        for method in (0, 1):
+            i, j = orc.neighbour_pairs(p, cell, sp, 3, cut, method=method)
+            assert len(i) > 20 and np.array_equal(i, i2[o]) and np.array_equal(j, j2[o])
+
+
 def test_zif4_bad_golden(zif4):
     g = GOLD["bad_N_Zn_N@2.5"]
     cut = np.zeros((4, 4))
