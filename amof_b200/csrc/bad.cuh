@@ -103,9 +103,8 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad(BadArgs a) {
                     if (dd < a.r2search) {
                         const int sj = (int)(o.s & 0xff);
                         if (dd < __ldg(a.cn_thr2 + krow[sj])) {
-                            if (nn < BAD_NB_MAX) {
-                                const double n = sqrt(dd);          // P6: u = v / |v|, componentwise
-                                ux[nn] = dx / n; uy[nn] = dy / n; uz[nn] = dz / n;
+                            if (nn < BAD_NB_MAX) {                  // keep the raw image vector; it is normalised after the walk
+                                ux[nn] = dx; uy[nn] = dy; uz[nn] = dz;
                                 sp[nn] = (unsigned char)sj;
                                 ++nn;
                             } else overflow = true;
@@ -117,6 +116,14 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad(BadArgs a) {
     }
     if (overflow) { atomicOr(a.flags, 1); return; }
     if (nn < 2) return;
+    // P6: u = v / |v|, componentwise.  Done here, once per kept neighbour and only for centres that can form an angle:
+    // inside the divergent candidate loop the sqrt and the three divisions (~160 instructions) ran whenever ANY lane
+    // of the warp had a hit.  |v|^2 is re-formed from the stored components in the same order, so n is the same double.
+    for (int p = 0; p < nn; ++p) {
+        const double dx = ux[p], dy = uy[p], dz = uz[p];
+        const double n = sqrt((dx * dx + dy * dy) + dz * dz);
+        ux[p] = dx / n; uy[p] = dy / n; uz[p] = dz / n;
+    }
     for (int t = 0; t < a.n_triples; ++t) {
         if (!((mine >> t) & 1ull)) continue;
         const int B = a.triples[t].y;
