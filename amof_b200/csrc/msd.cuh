@@ -435,10 +435,18 @@ __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *
             if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
                 const double2 *p2 = reinterpret_cast<const double2 *>(p);
                 const int n2 = (3 * T) >> 1;
+                // prepare: the centre of mass [T][3] has the layout of the series itself, so the shift p - com is taken here,
+                // element by element, with the same coalesced access (com stays in L2)
+                const double2 *c2 = reinterpret_cast<const double2 *>(com);
                 for (int i0 = threadIdx.x; i0 < n2; i0 += 8 * blockDim.x) {
                     double2 v[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) if (i0 + u * blockDim.x < n2) v[u] = __ldg(p2 + i0 + u * blockDim.x);
+                    if (prepare) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (i0 + u * blockDim.x < n2) { const double2 c = __ldg(c2 + i0 + u * blockDim.x); v[u].x -= c.x; v[u].y -= c.y; }
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int i = i0 + u * blockDim.x;
@@ -450,9 +458,9 @@ __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *
                         }
                     }
                 }
-                if ((3 * T) & 1) { if (threadIdx.x == 0) sm[2 * tp + (T - 1)] = p[3 * T - 1]; }
+                if ((3 * T) & 1) { if (threadIdx.x == 0) sm[2 * tp + (T - 1)] = p[3 * T - 1] - (prepare ? com[3 * T - 1] : 0.0); }
             } else {
-                for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) { const int f = i / 3; sm[(i - 3 * f) * tp + f] = p[i]; }
+                for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) { const int f = i / 3; sm[(i - 3 * f) * tp + f] = p[i] - (prepare ? com[i] : 0.0); }
             }
             if (a + 1 < a_hi) {                             // pull the next series into L2 while this one is worked on
                 const char *nx = reinterpret_cast<const char *>(p + (size_t)T * 3);
@@ -467,12 +475,8 @@ __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *
                 // in parallel over frames first, with coalesced centre-of-mass reads, is 8 % slower on C5.)
                 const int C = ((T + (int)blockDim.x - 1) / (int)blockDim.x) | 1;
                 const int k0 = threadIdx.x * C, k1 = min(T, k0 + C);
-                double px = 0.0, py = 0.0, pz = 0.0;        // shifted position of the frame before my first one
-                if (k0 >= 1 && k0 < T) {
-                    px = sm[k0 - 1] - com[3 * (size_t)(k0 - 1)];
-                    py = sm[tp + k0 - 1] - com[3 * (size_t)(k0 - 1) + 1];
-                    pz = sm[2 * tp + k0 - 1] - com[3 * (size_t)(k0 - 1) + 2];
-                }
+                double px = 0.0, py = 0.0, pz = 0.0;        // (shifted) position of the frame before my first one
+                if (k0 >= 1 && k0 < T) { px = sm[k0 - 1]; py = sm[tp + k0 - 1]; pz = sm[2 * tp + k0 - 1]; }
                 __syncthreads();                            // every predecessor is read before anybody overwrites it
                 double sx = 0.0, sy = 0.0, sz = 0.0;
                 {
@@ -480,8 +484,9 @@ __global__ void __launch_bounds__(MSD_AP_THREADS) k_msd_window_ap(const double *
                     if (CELL == 1) g0 = geom[0];
                     double i0 = 0.0, i4 = 0.0, i8 = 0.0, c0 = 0.0, c4 = 0.0, c8 = 0.0;
                     if (CELL == 2) { i0 = geom[0].inv[0]; i4 = geom[0].inv[4]; i8 = geom[0].inv[8]; c0 = geom[0].cell[0]; c4 = geom[0].cell[4]; c8 = geom[0].cell[8]; }
+                    // (Measured: four frames per trip with their wraps overlapped is 20 % slower -- register spills.)
                     for (int k = k0; k < k1; ++k) {
-                        const double x = sm[k] - com[3 * (size_t)k], y = sm[tp + k] - com[3 * (size_t)k + 1], z = sm[2 * tp + k] - com[3 * (size_t)k + 2];
+                        const double x = sm[k], y = sm[tp + k], z = sm[2 * tp + k];       // already shifted by the centre of mass
                         double dx, dy, dz;
                         if (k == 0) { dx = x; dy = y; dz = z; }                                     // delta_0 = first positions
                         else if (CELL == 2) wrap_disp_diag(i0, i4, i8, c0, c4, c8, x - px, y - py, z - pz, dx, dy, dz);
