@@ -34,6 +34,9 @@
 #ifndef TILE_PAIRED
 #define TILE_PAIRED 1
 #endif
+#ifndef TILE_QUAD
+#define TILE_QUAD 0
+#endif
 #define TILE_PRAGMA_(x) _Pragma(#x)
 #define TILE_PRAGMA_UNROLL(n) TILE_PRAGMA_(unroll n)
 #define TILE_MAX_ENTRIES 1024     // rows x virtual cells per tile
@@ -341,6 +344,33 @@ __device__ __forceinline__ void scan_run(const PairArgs &a, const SAtom *__restr
         if (HAS_CN && dd < cn_r2max && dd < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
     };
     unsigned addr = abase + (unsigned)(jb + sub) * 32u;
+#if TILE_QUAD
+    // four candidates per trip (measured against two: see DESIGN.md section 8)
+    for (; addr + 3u * astep < aend; addr += 4u * astep) {
+        const unsigned addr1 = addr + astep, addr2 = addr1 + astep, addr3 = addr2 + astep;
+        double ox0, oy0, oz0, ox1, oy1, oz1, ox2, oy2, oz2, ox3, oy3, oz3;
+        lds_xyz(addr, ox0, oy0, oz0);
+        lds_xyz(addr1, ox1, oy1, oz1);
+        lds_xyz(addr2, ox2, oy2, oz2);
+        lds_xyz(addr3, ox3, oy3, oz3);
+        double dx0 = ox0 - me.x, dy0 = oy0 - me.y, dz0 = oz0 - me.z;
+        double dx1 = ox1 - me.x, dy1 = oy1 - me.y, dz1 = oz1 - me.z;
+        double dx2 = ox2 - me.x, dy2 = oy2 - me.y, dz2 = oz2 - me.z;
+        double dx3 = ox3 - me.x, dy3 = oy3 - me.y, dz3 = oz3 - me.z;
+        if (SHIFT) {
+            dx0 += Tx; dy0 += Ty; dz0 += Tz; dx1 += Tx; dy1 += Ty; dz1 += Tz;
+            dx2 += Tx; dy2 += Ty; dz2 += Tz; dx3 += Tx; dy3 += Ty; dz3 += Tz;
+        }
+        const double dd0 = (dx0 * dx0 + dy0 * dy0) + dz0 * dz0;
+        const double dd1 = (dx1 * dx1 + dy1 * dy1) + dz1 * dz1;
+        const double dd2 = (dx2 * dx2 + dy2 * dy2) + dz2 * dz2;
+        const double dd3 = (dx3 * dx3 + dy3 * dy3) + dz3 * dz3;
+        if (dd0 < r2search && !(AFTER && addr <= askip)) hit(addr, dd0);
+        if (dd1 < r2search && !(AFTER && addr1 <= askip)) hit(addr1, dd1);
+        if (dd2 < r2search && !(AFTER && addr2 <= askip)) hit(addr2, dd2);
+        if (dd3 < r2search && !(AFTER && addr3 <= askip)) hit(addr3, dd3);
+    }
+#endif
 #if TILE_PAIRED
     // two candidates per trip: both distance chains are in flight together (the fp64 chain is latency-bound at
     // 8 warps per scheduler), and the loop overhead is paid once per pair
