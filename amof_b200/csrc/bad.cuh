@@ -69,6 +69,42 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad(BadArgs a) {
     bool overflow = false;
     const double mex = me.x, mey = me.y, mez = me.z;
     const uint16_t *krow = a.keyidx + si * S;
+    // the z window [c2 - m2, c2 + m2] is the same for every row of the stencil: split it once into its contiguous
+    // runs (one per wrap of the column; a third wrap only happens in boxes narrower than the stencil)
+    int zq[3], zl[3], zs[3], nz = 0;
+    bool many_wraps = false;
+    for (int d2 = -m2; d2 <= m2;) {
+        int s2, q2;
+        wrap_cell(c2 + d2, nc2, s2, q2);
+        const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
+        if (nz < 3) { zq[nz] = q2; zl[nz] = len; zs[nz] = s2; ++nz; } else many_wraps = true;
+        d2 += len;
+    }
+    auto scan_run = [&](int rowbase, int s01, double Rx, double Ry, double Rz, int q2, int len, int s2) {
+        const int jb = (int)cs[rowbase + q2], je = (int)cs[rowbase + q2 + len];
+        if (je <= jb) return;
+        const bool self_image = ((s01 | s2) == 0);
+        double Tx = Rx, Ty = Ry, Tz = Rz;          // (0 + 0) + s2*c == s2*c and x + 0.0 == x: same bits as the full P3 sum
+        if (s2 != 0) { const double fs2 = (double)s2; Tx = Rx + fs2 * G.cell[6]; Ty = Ry + fs2 * G.cell[7]; Tz = Rz + fs2 * G.cell[8]; }
+        for (int j = jb; j < je; ++j) {
+            if (self_image && j == i) continue;
+            const SAtom o = load_satom(fr + j);
+            const double dx = (o.x - mex) + Tx;
+            const double dy = (o.y - mey) + Ty;
+            const double dz = (o.z - mez) + Tz;
+            const double dd = (dx * dx + dy * dy) + dz * dz;
+            if (dd < a.r2search) {
+                const int sj = (int)(o.s & 0xff);
+                if (dd < __ldg(a.cn_thr2 + krow[sj])) {
+                    if (nn < BAD_NB_MAX) {                  // keep the raw image vector; it is normalised after the walk
+                        ux[nn] = dx; uy[nn] = dy; uz[nn] = dz;
+                        sp[nn] = (unsigned char)sj;
+                        ++nn;
+                    } else overflow = true;
+                }
+            }
+        }
+    };
     for (int d0 = -m0; d0 <= m0; ++d0) {
         int s0, q0;
         wrap_cell(c0 + d0, nc0, s0, q0);
@@ -82,34 +118,15 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad(BadArgs a) {
                 const double fs0 = (double)s0, fs1 = (double)s1;
                 Rx = fs0 * G.cell[0] + fs1 * G.cell[3]; Ry = fs0 * G.cell[1] + fs1 * G.cell[4]; Rz = fs0 * G.cell[2] + fs1 * G.cell[5];
             }
-            int d2 = -m2;
-            while (d2 <= m2) {
-                int s2, q2;
-                wrap_cell(c2 + d2, nc2, s2, q2);
-                const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
-                const int jb = (int)cs[rowbase + q2], je = (int)cs[rowbase + q2 + len];
-                d2 += len;
-                if (je <= jb) continue;
-                const bool self_image = ((s0 | s1 | s2) == 0);
-                double Tx = Rx, Ty = Ry, Tz = Rz;          // (0 + 0) + s2*c == s2*c and x + 0.0 == x: same bits as the full P3 sum
-                if (s2 != 0) { const double fs2 = (double)s2; Tx = Rx + fs2 * G.cell[6]; Ty = Ry + fs2 * G.cell[7]; Tz = Rz + fs2 * G.cell[8]; }
-                for (int j = jb; j < je; ++j) {
-                    if (self_image && j == i) continue;
-                    const SAtom o = load_satom(fr + j);
-                    const double dx = (o.x - mex) + Tx;
-                    const double dy = (o.y - mey) + Ty;
-                    const double dz = (o.z - mez) + Tz;
-                    const double dd = (dx * dx + dy * dy) + dz * dz;
-                    if (dd < a.r2search) {
-                        const int sj = (int)(o.s & 0xff);
-                        if (dd < __ldg(a.cn_thr2 + krow[sj])) {
-                            if (nn < BAD_NB_MAX) {                  // keep the raw image vector; it is normalised after the walk
-                                ux[nn] = dx; uy[nn] = dy; uz[nn] = dz;
-                                sp[nn] = (unsigned char)sj;
-                                ++nn;
-                            } else overflow = true;
-                        }
-                    }
+            if (!many_wraps) {
+                for (int k = 0; k < nz; ++k) scan_run(rowbase, s0 | s1, Rx, Ry, Rz, zq[k], zl[k], zs[k]);
+            } else {
+                for (int d2 = -m2; d2 <= m2;) {
+                    int s2, q2;
+                    wrap_cell(c2 + d2, nc2, s2, q2);
+                    const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
+                    scan_run(rowbase, s0 | s1, Rx, Ry, Rz, q2, len, s2);
+                    d2 += len;
                 }
             }
         }
