@@ -570,6 +570,20 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     int cell_div = env_int("AMOFB_CELL_DIV", p->has_rdf ? 2 : 1);
     if (cell_div < 1) cell_div = 1;
     if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, p->has_cn ? p->nkeys : 0))) return fail(rc);
+    if (!p->has_rdf && !env_int("AMOFB_CN_NO_FILTER", 0)) {
+        // counts only (amof.cn): a species without a positive cutoff towards any species can neither count nor be counted,
+        // so it never enters the cell list (as for the bond angles)
+        uint8_t keep[AMOFB_MAX_SPECIES];
+        memset(keep, 0, sizeof keep);
+        for (int x = 0; x < S; ++x)
+            for (int y = 0; y < S; ++y)
+                if (cn_cutoff[x * S + y] > 0.0) keep[x] = 1;
+        int n_keep = 0;
+        for (int i = 0; i < n_atoms; ++i) n_keep += keep[species[i]];
+        p->bt.n_keep = n_keep;
+        if ((rc = dev_alloc(ctx, &p->bt.d_species_keep, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
+        cudaMemcpy(p->bt.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice);
+    }
     if ((rc = dev_alloc(ctx, &p->d_edge2, edge2.size()))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_keyidx, keyidx.size()))) return fail(rc);
@@ -731,7 +745,8 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
         a.slabs = p->d_slabs; a.ghist = p->d_hist; a.cn_out = s->d_out;
         a.r2search = p->r2search; a.r2max = p->r2max; a.inv_dr_f = p->inv_dr_f; a.bin_margin = p->bin_margin; a.cn_r2max = p->cn_r2max;
         a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys; a.nbins = p->nbins;
-        a.tiles_per_frame = (b.n_atoms + PAIR_TILE - 1) / PAIR_TILE;
+        a.n_sorted = b.n_keep;
+        a.tiles_per_frame = (b.n_keep + PAIR_TILE - 1) / PAIR_TILE;
         a.hard_mask = nullptr; a.n_hard = nullptr;
         long long tiles = (long long)nf * a.tiles_per_frame;
         if (tiles > 0) {

@@ -37,6 +37,7 @@ struct PairArgs {
     float bin_margin;             // see rdf_bin
     int n_atoms, n_frames, n_species, nkeys, nbins;
     int tiles_per_frame;
+    int n_sorted;                 // atoms per frame in the cell list (< n_atoms when the species filter of a CN-only analysis is on)
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(PAIR_TILE, 2) k_pair(PairArgs a) {
             reinterpret_cast<int *>(&s_geom)[threadIdx.x] = reinterpret_cast<const int *>(&a.geom[f])[threadIdx.x];
         __syncthreads();
         const int i = tin * PAIR_TILE + threadIdx.x;   // sorted index inside the frame
-        if (i < a.n_atoms) {
+        if (i < a.n_sorted) {
             const SAtom *fr = a.sorted + (long long)f * a.n_atoms;
             const uint32_t *cs = a.cell_start + s_geom.cs_off;
             const SAtom me = load_satom(fr + i);
