@@ -16,6 +16,7 @@
  * Reference call sites restated here:
  *   RDF   amof/rdf.py:67-114      (asap3 RadialDistributionFunction(atoms, rMax, nBins).update())
  *   CN    amof/cn.py:48-82        + amof/atom.py:72-87 (ase.neighborlist.neighbor_list('ij', atoms, cutoff_dict))
+ *   NL    amof/atom.py:72-87      (the same neighbour list, returned as pairs: orc_neighbour_pairs)
  *   BAD   amof/bad.py:70-160,192-300 (Atoms.get_angles(idx, mic=True), np.histogram(edges))
  *   MSD   amof/msd.py:186-268     + amof/trajectory.py:285-303 (ase wrap_positions(center=(0,0,0)))
  *
