@@ -103,6 +103,27 @@ def test_window_msd_fixed_cell(backend, tri, unwrap):
         np.testing.assert_allclose(new_pos - com[:, None, :], mutated, rtol=0, atol=1e-9)
 
 
+def test_window_msd_long_series_properties(backend, monkeypatch):
+    """A C5-shaped request (unwrapped random walk, fixed orthorhombic box, window = arange(0, T//2, 50)) at a size the
+    oracle does not finish in seconds: the tiled kernel must agree with the generic one to 1e-12 and follow the
+    random-walk law MSD(m) = 3 sigma^2 m (T-m-1)/(T-m) (quirk Q4) within the sampling noise."""
+    T, n, S, sigma = 1200, 3000, 4, 0.05
+    rng = np.random.default_rng(5)
+    pos = 100.0 + np.cumsum(rng.normal(scale=sigma, size=(T, n, 3)), axis=0)
+    cells = np.broadcast_to(np.diag([231.0, 246.0, 277.0]), (T, 3, 3)).copy()
+    spec = (np.arange(n) % S).astype(np.uint8)
+    masses = np.array([1.008, 12.011, 14.007, 65.38])[spec]
+    window = np.arange(0, T // 2, 50)
+    tiled, _, _ = _gpu_window(backend, pos, cells, spec, masses, S, window, False)
+    monkeypatch.setenv("AMOFB_MSD_NO_AP", "1")
+    generic, _, _ = _gpu_window(backend, pos, cells, spec, masses, S, window, False)
+    np.testing.assert_allclose(tiled, generic, rtol=RTOL, atol=1e-13)
+    m = window.astype(np.float64)
+    law = 3.0 * sigma ** 2 * m * (T - m - 1) / (T - m)
+    assert np.all(tiled[:, 0] == 0.0)
+    np.testing.assert_allclose(tiled[:, 1:].mean(axis=0), law[1:], rtol=0.05)      # COM removal costs O(1/n)
+
+
 def test_window_msd_irregular_windows(backend):
     """window lengths that are NOT an arithmetic progression (only reachable through the C ABI) -> generic kernel;
     lengths >= T contribute nothing"""
