@@ -513,6 +513,11 @@ def run_msd(args, backend, rank, world):
     for k, v in u.items():
         out[k] = v
         out[k.replace("_per_step", "_per_s")] = v * args.steps * world / (dev_ms / 1e3)
+    if "atom_frame_pairs_per_step" in u:
+        # the tiled window kernel issues 6 FP64 instructions per frame pair (3 differences + 3 chained FMAs)
+        ginstr = 6.0 * u["atom_frame_pairs_per_step"] * args.steps / (dev_ms / 1e3) / 1e9
+        out["roofline"]["fp64"] = {"achieved_ginstr": ginstr, "peak_ginstr": FP64_NOFMA_GOPS, "frac": ginstr / FP64_NOFMA_GOPS,
+                                   "instr_per_pair": 6, "peak_source": "tools/microbench.cu FP64 issue rate, measured on this pool"}
     if world == 1:
         from oracle import c_oracle as orc
         dt = wl.cpu_sample(1, min(wl.T, 400))
