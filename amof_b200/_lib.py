@@ -67,6 +67,7 @@ SIGNATURES = {
     "amofb_bad_finish": (C.c_int, [_vp, _u64p, _u64p, _i64p]),
     "amofb_neigh_count": (C.c_int, [_vp, C.c_int, C.c_int, _u8p, _dp, _dp, _dp, _i64p]),
     "amofb_neigh_fill": (C.c_int, [_vp, C.POINTER(C.c_int32), C.c_int64]),
+    "amofb_neigh_fill_ex": (C.c_int, [_vp, C.POINTER(C.c_int32), _dp, C.POINTER(C.c_int32), C.c_int64]),
     "amofb_msd_begin": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _u8p, C.c_int, _dp]),
     "amofb_msd_load": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "amofb_msd_load_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -295,9 +296,10 @@ class GpuBackend:
         return hist, dropped, int(nf.value)
 
     # -- explicit neighbour list --------------------------------------------------------------------
-    def neighbour_list(self, species, n_species, positions, cell, cutoff):
+    def neighbour_list(self, species, n_species, positions, cell, cutoff, quantities=False):
         """One frame -> (offsets int64[n+1], neighbours int32[offsets[n]]): row i = neighbours[offsets[i]:offsets[i+1]],
-        ascending original indices, one entry per periodic image under cutoff[Zi][Zj] (amof/atom.py:72-87)."""
+        ascending original indices, one entry per periodic image under cutoff[Zi][Zj] (amof/atom.py:72-87).
+        ``quantities=True`` adds (distances float64[...], shifts int32[...][3]): ase's 'd' and 'S' of every pair."""
         ctx, lib = self.ctx, self.ctx.lib
         species = np.ascontiguousarray(species, dtype=np.uint8)
         S = int(n_species)
@@ -307,9 +309,17 @@ class GpuBackend:
         offsets = np.zeros(len(species) + 1, dtype=np.int64)
         ctx.check(lib.amofb_neigh_count(ctx.h, len(species), S, _ptr(species, _u8p), _ptr(cut, _dp), _ptr(pos, _dp),
                                         _ptr(cell, _dp), _ptr(offsets, _i64p)))
-        nbr = np.zeros(int(offsets[-1]), dtype=np.int32)
-        ctx.check(lib.amofb_neigh_fill(ctx.h, _ptr(nbr, C.POINTER(C.c_int32)) if len(nbr) else None, len(nbr)))
-        return offsets, nbr
+        total = int(offsets[-1])
+        nbr = np.zeros(total, dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        if not quantities:
+            ctx.check(lib.amofb_neigh_fill(ctx.h, _ptr(nbr, i32p) if total else None, total))
+            return offsets, nbr
+        dist = np.zeros(total, dtype=np.float64)
+        shifts = np.zeros((total, 3), dtype=np.int32)
+        ctx.check(lib.amofb_neigh_fill_ex(ctx.h, _ptr(nbr, i32p) if total else None, _ptr(dist, _dp) if total else None,
+                                          _ptr(shifts, i32p) if total else None, total))
+        return offsets, nbr, dist, shifts
 
     # -- MSD --------------------------------------------------------------------------------------
     def msd_open(self, n_frames, masses, species, n_species, cells):

@@ -49,23 +49,26 @@ def format_cutoff(nb_set_and_cutoff, format='ase', sort_pair=False):
         return cutoff_dict
 
 
-def get_neighborlist_csr(atom, cutoff_dict, backend=None):
+def get_neighborlist_csr(atom, cutoff_dict, backend=None, quantities=False):
     """Neighbour list of one frame in CSR form: ``(offsets int64[n+1], neighbours int32[offsets[n]])``.
 
     Same pairs as ``ase.neighborlist.neighbor_list('ij', atom, cutoff_dict)`` (amof/atom.py:82): j is a neighbour of
     i iff d < cutoff[(Zi, Zj)] (both key orders, unlisted pairs never), once per periodic image, without the
-    zero-shift self pair.  Inside a row the indices are ascending (ase leaves that order unspecified)."""
+    zero-shift self pair.  Inside a row the pairs are ordered by (j, S) (ase leaves that order unspecified).
+    ``quantities=True`` appends ``(distances, shifts)``: ase's 'd' and 'S' (D = p_j - p_i + S.cell), the quantities
+    ``pymatgen.Structure.get_neighbor_list`` returns to amof.coordination (coordination/core.py:62,181)."""
     from . import _lib, frames
     backend = backend or _lib.get_backend()
     numbers = np.asarray(atom.get_atomic_numbers())
     zs, spec = frames.species_index(numbers)
     cut = cutoff_matrix(cutoff_dict, zs)
-    return backend.neighbour_list(spec, len(zs), atom.get_positions(), np.asarray(atom.get_cell(), dtype=np.float64), cut)
+    return backend.neighbour_list(spec, len(zs), atom.get_positions(), np.asarray(atom.get_cell(), dtype=np.float64), cut,
+                                  quantities=quantities)
 
 
 def get_neighborlist(atom, cutoff_dict, backend=None):
     """list (one entry per atom) of lists of neighbour indices, as amof.atom.get_neighborlist (atom.py:72-87)"""
-    offsets, nbr = get_neighborlist_csr(atom, cutoff_dict, backend)
+    offsets, nbr = get_neighborlist_csr(atom, cutoff_dict, backend)[:2]
     flat = nbr.tolist()
     off = offsets.tolist()
     return [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]

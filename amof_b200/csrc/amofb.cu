@@ -258,6 +258,7 @@ struct BatchSlot {
     uint32_t *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cid = nullptr, *d_rank = nullptr;
     SAtom *d_sorted = nullptr;
     uint32_t *d_orig = nullptr;            // only when the batcher was asked for it (want_orig)
+    int *d_wraps = nullptr;                // idem: [frames][n_atoms][3]
     unsigned long long *d_out = nullptr, *h_out = nullptr;   // per-frame outputs of the batch
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     int frames = 0;        // frames of the batch in flight (0 = idle)
@@ -284,7 +285,7 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
     for (auto &s : b.slot) {
         pool_put(ctx, s.d_raw); pool_put(ctx, s.d_geom); pool_put(ctx, s.h_geom);
         pool_put(ctx, s.d_cell_count); pool_put(ctx, s.d_cell_start); pool_put(ctx, s.d_cid); pool_put(ctx, s.d_rank);
-        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
+        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_wraps); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
@@ -318,6 +319,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
         AMOFB_TRY(dev_alloc(ctx, &s.d_rank, na));
         AMOFB_TRY(dev_alloc(ctx, &s.d_sorted, na));
         if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_orig, na));
+        if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_wraps, na * 3));
         if (per_frame_out > 0) {
             AMOFB_TRY(dev_alloc(ctx, &s.d_out, (size_t)b.cap_frames * per_frame_out));
             AMOFB_TRY(pinned_alloc(ctx, &s.h_out, (size_t)b.cap_frames * per_frame_out));
@@ -378,6 +380,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.sorted = s.d_sorted; pa.n_atoms = b.n_atoms; pa.n_frames = nf;
     pa.species_keep = b.d_species_keep;
     pa.orig = s.d_orig;
+    pa.wraps = s.d_wraps;
     long long total = (long long)nf * b.n_atoms;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;

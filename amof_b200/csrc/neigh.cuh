@@ -8,7 +8,8 @@
 // d2 < cn_thr2[key] (P5: the bisected d2 threshold of `sqrt(d2) < cutoff`), the zero-shift self pair is skipped and the
 // same j under several periodic images appears once per image, as ase lists it.
 //   FILL = false: count[i] = number of neighbours of atom i (original index)
-//   FILL = true : the thread writes its row nbr[offset[i] ...] with ORIGINAL indices and sorts it ascending in place
+//   FILL = true : the thread writes its row nbr[offset[i] ...] with ORIGINAL indices (optionally the distance and the
+//                 image shift of every pair) and sorts it in place by (j, S)
 #pragma once
 #include "prep.cuh"
 
@@ -22,6 +23,9 @@ struct NeighArgs {
     int *count;                   // [n_atoms]
     const long long *offset;      // [n_atoms + 1]
     int *nbr;                     // [offset[n_atoms]]
+    const int *wraps;             // [n_keep][3] cell translations P2 removed from every sorted atom
+    double *dist;                 // optional [offset[n_atoms]]: sqrt(d2) of every listed pair (ase's 'd')
+    int *shifts;                  // optional [offset[n_atoms]][3]: S with D = p_j - p_i + S.cell for the ORIGINAL positions ('S')
     double r2search;
     int n_atoms, n_keep, n_species;
 };
@@ -41,7 +45,8 @@ __global__ void __launch_bounds__(128) k_neigh(NeighArgs a) {
     const uint16_t *krow = a.keyidx + si * a.n_species;
     const int io = (int)a.orig[i];
     int *row = nullptr;
-    if (FILL) row = a.nbr + a.offset[io];
+    long long base = 0;
+    if (FILL) { base = a.offset[io]; row = a.nbr + base; }
     int nn = 0;
     for (int d0 = -m0; d0 <= m0; ++d0) {
         int s0, q0;
@@ -71,7 +76,17 @@ __global__ void __launch_bounds__(128) k_neigh(NeighArgs a) {
                     const double dz = (o.z - me.z) + Tz;
                     const double dd = (dx * dx + dy * dy) + dz * dz;
                     if (dd < a.r2search && dd < __ldg(a.cn_thr2 + krow[(int)(o.s & 0xff)])) {
-                        if (FILL) row[nn] = (int)a.orig[j];
+                        if (FILL) {
+                            row[nn] = (int)a.orig[j];
+                            if (a.dist) a.dist[base + nn] = sqrt(dd);
+                            if (a.shifts) {
+                                // the search shifts the WRAPPED positions pw = p - w.cell:  dv = (p_j - p_i) + (S + w_i - w_j).cell
+                                int *sp = a.shifts + 3 * (base + nn);
+                                sp[0] = s0 + a.wraps[3 * i] - a.wraps[3 * j];
+                                sp[1] = s1 + a.wraps[3 * i + 1] - a.wraps[3 * j + 1];
+                                sp[2] = s2 + a.wraps[3 * i + 2] - a.wraps[3 * j + 2];
+                            }
+                        }
                         ++nn;
                     }
                 }
@@ -79,10 +94,30 @@ __global__ void __launch_bounds__(128) k_neigh(NeighArgs a) {
         }
     }
     if (!FILL) { a.count[io] = nn; return; }
-    for (int p = 1; p < nn; ++p) {            // rows are a handful of entries: insertion sort by the owning thread
-        const int v = row[p];
+    // rows are a handful of entries: insertion sort by the owning thread, keyed by (j, S) so that the several images of
+    // one partner come out in a defined order; distances and shifts move with their pair
+    auto before = [&](int vj, int v0, int v1, int v2, long long q) {      // is (vj, v) < entry q ?
+        if (vj != row[q]) return vj < row[q];
+        if (!a.shifts) return false;
+        const int *sq = a.shifts + 3 * (base + q);
+        if (v0 != sq[0]) return v0 < sq[0];
+        if (v1 != sq[1]) return v1 < sq[1];
+        return v2 < sq[2];
+    };
+    for (int p = 1; p < nn; ++p) {
+        const int vj = row[p];
+        const double vd = a.dist ? a.dist[base + p] : 0.0;
+        int v0 = 0, v1 = 0, v2 = 0;
+        if (a.shifts) { const int *sp = a.shifts + 3 * (base + p); v0 = sp[0]; v1 = sp[1]; v2 = sp[2]; }
         int q = p - 1;
-        while (q >= 0 && row[q] > v) { row[q + 1] = row[q]; --q; }
-        row[q + 1] = v;
+        while (q >= 0 && before(vj, v0, v1, v2, q)) {
+            row[q + 1] = row[q];
+            if (a.dist) a.dist[base + q + 1] = a.dist[base + q];
+            if (a.shifts) { int *d = a.shifts + 3 * (base + q + 1); const int *s = d - 3; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+            --q;
+        }
+        row[q + 1] = vj;
+        if (a.dist) a.dist[base + q + 1] = vd;
+        if (a.shifts) { int *d = a.shifts + 3 * (base + q + 1); d[0] = v0; d[1] = v1; d[2] = v2; }
     }
 }

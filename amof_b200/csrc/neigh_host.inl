@@ -27,6 +27,7 @@ static NeighArgs neigh_args(NeighState *p) {
     NeighArgs a;
     a.sorted = p->slot->d_sorted; a.geom = p->slot->d_geom; a.cell_start = p->slot->d_cell_start; a.orig = p->slot->d_orig;
     a.cn_thr2 = p->d_cnthr2; a.keyidx = p->d_keyidx; a.count = p->d_count; a.offset = p->d_offset; a.nbr = nullptr;
+    a.wraps = p->slot->d_wraps; a.dist = nullptr; a.shifts = nullptr;
     a.r2search = p->r2search; a.n_atoms = p->bt.n_atoms; a.n_keep = p->bt.n_keep; a.n_species = p->n_species;
     return a;
 }
@@ -114,7 +115,7 @@ extern "C" int amofb_neigh_count(amofb_ctx *ctx, int n_atoms, int n_species, con
     return AMOFB_OK;
 }
 
-extern "C" int amofb_neigh_fill(amofb_ctx *ctx, int32_t *neighbors, int64_t capacity) {
+extern "C" int amofb_neigh_fill_ex(amofb_ctx *ctx, int32_t *neighbors, double *distances, int32_t *shifts, int64_t capacity) {
     if (!ctx) return AMOFB_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     NeighState *p = ctx->neigh;
@@ -124,18 +125,27 @@ extern "C" int amofb_neigh_fill(amofb_ctx *ctx, int32_t *neighbors, int64_t capa
         amofb_fail(ctx, AMOFB_ERR_ARG, "neighbour buffer holds %lld entries, %lld are needed", (long long)capacity, p->total);
         return fail(AMOFB_ERR_ARG);
     }
-    int *d_nbr = nullptr;
+    int *d_nbr = nullptr, *d_shifts = nullptr;
+    double *d_dist = nullptr;
     int rc = dev_alloc(ctx, &d_nbr, (size_t)p->total);
-    if (rc) return fail(rc);
+    if (!rc && distances) rc = dev_alloc(ctx, &d_dist, (size_t)p->total);
+    if (!rc && shifts) rc = dev_alloc(ctx, &d_shifts, (size_t)p->total * 3);
+    if (rc) { pool_put(ctx, d_nbr); pool_put(ctx, d_dist); pool_put(ctx, d_shifts); return fail(rc); }
     NeighArgs a = neigh_args(p);
-    a.nbr = d_nbr;
+    a.nbr = d_nbr; a.dist = d_dist; a.shifts = d_shifts;
     k_neigh<true><<<(p->bt.n_keep + 127) / 128, 128, 0, ctx->s_compute>>>(a);
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(neighbors, d_nbr, sizeof(int) * (size_t)p->total, cudaMemcpyDeviceToHost, ctx->s_compute);
+    if (e == cudaSuccess && distances) e = cudaMemcpyAsync(distances, d_dist, sizeof(double) * (size_t)p->total, cudaMemcpyDeviceToHost, ctx->s_compute);
+    if (e == cudaSuccess && shifts) e = cudaMemcpyAsync(shifts, d_shifts, sizeof(int) * 3 * (size_t)p->total, cudaMemcpyDeviceToHost, ctx->s_compute);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
-    pool_put(ctx, d_nbr);
+    pool_put(ctx, d_nbr); pool_put(ctx, d_dist); pool_put(ctx, d_shifts);
     if (e != cudaSuccess) { amofb_fail(ctx, AMOFB_ERR_CUDA, "neigh_fill: %s", cudaGetErrorString(e)); return fail(AMOFB_ERR_CUDA); }
     neigh_release(ctx);
     return AMOFB_OK;
+}
+
+extern "C" int amofb_neigh_fill(amofb_ctx *ctx, int32_t *neighbors, int64_t capacity) {
+    return amofb_neigh_fill_ex(ctx, neighbors, nullptr, nullptr, capacity);
 }

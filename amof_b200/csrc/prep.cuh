@@ -38,9 +38,11 @@ struct PrepArgs {
     // neither be a centre nor a neighbour under the cutoff matrix, so the sorted frame holds cell_start[ncell] atoms
     const uint8_t *species_keep;   // [n_species] or nullptr
     uint32_t *orig;                // optional [F*N]: original atom index of every sorted atom (explicit neighbour lists)
+    int *wraps;                    // optional [F*N][3]: cell translations removed from every sorted atom by P2
 };
 
-__device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__restrict__ p, double *pw, int *c) {
+// wn (optional): the integer cell translations w_k = floor(f_k) that P2 removed
+__device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__restrict__ p, double *pw, int *c, int *wn = nullptr) {
     double px = p[0], py = p[1], pz = p[2];
     double f[3], w[3];
 #pragma unroll
@@ -58,6 +60,7 @@ __device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__re
         if (ck > g.nc[k] - 1) ck = g.nc[k] - 1;
         c[k] = ck;
     }
+    if (wn) { wn[0] = (int)w[0]; wn[1] = (int)w[1]; wn[2] = (int)w[2]; }
 }
 
 __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
@@ -149,8 +152,8 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         if (a.cid[idx] == 0xffffffffu) continue;          // filtered out by species_keep
         const FrameGeom &g = a.geom[f];
         double pw[3];
-        int c[3];
-        wrap_atom(g, a.raw + 3 * idx, pw, c);
+        int c[3], wn[3];
+        wrap_atom(g, a.raw + 3 * idx, pw, c, wn);
         uint32_t dst = a.cell_start[g.cs_off + a.cid[idx]] + a.rank[idx];
         SAtom s;
         s.x = pw[0]; s.y = pw[1]; s.z = pw[2];
@@ -158,5 +161,9 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
         if (a.orig) a.orig[(long long)f * a.n_atoms + dst] = (uint32_t)i;
+        if (a.wraps) {
+            int *wp = a.wraps + 3 * ((long long)f * a.n_atoms + dst);
+            wp[0] = wn[0]; wp[1] = wn[1]; wp[2] = wn[2];
+        }
     }
 }

@@ -140,10 +140,15 @@ int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *dropped, int64_t 
  *         (offsets[n_atoms] = number of directed pairs).  The search state stays open for fill.
  * fill  : neighbors int32[capacity], capacity >= offsets[n_atoms]: row i = neighbors[offsets[i] .. offsets[i+1]),
  *         ORIGINAL atom indices in ascending order (ase's own order inside a row is unspecified).  Ends the search.
+ * fill_ex: the same plus, per listed pair and in the same order, ase's quantities 'd' and 'S' -- what
+ *         pymatgen's Structure.get_neighbor_list hands amof.coordination (/root/reference/amof/coordination/core.py:62,181):
+ *         distances double[capacity] (or NULL) = |D|, shifts int32[capacity][3] (or NULL) = the integer image S with
+ *         D = p_j - p_i + S.cell for the positions as given (not wrapped).  Rows are ordered by (j, S).
  */
 int amofb_neigh_count(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, const double *cutoff,
                       const double *pos, const double *cell, int64_t *offsets);
 int amofb_neigh_fill(amofb_ctx *ctx, int32_t *neighbors, int64_t capacity);
+int amofb_neigh_fill_ex(amofb_ctx *ctx, int32_t *neighbors, double *distances, int32_t *shifts, int64_t capacity);
 
 /* ---- mean-squared displacement --------------------------------------------------------------
  * Replaces WindowMsd.compute_msd / compute_msd_of_m and trajectory.get_delta_pos

@@ -355,28 +355,47 @@ int orc_cn_traj(int nframes, int n, const double *pos, const double *cell, const
 
 /* ------------------------------------------------------------------ explicit neighbour list (P5) */
 /* amof/atom.py:72-87: nl_i, nl_j = ase.neighborlist.neighbor_list('ij', atom, cutoff_dict).  Directed pairs (i, j),
- * one per periodic image with sqrt(d2) < cutoff[Zi][Zj]; the first `capacity` of them are stored, *count gets the total. */
+ * one per periodic image with sqrt(d2) < cutoff[Zi][Zj]; the first `capacity` of them are stored, *count gets the total.
+ * Optionally also ase's quantities 'd' and 'S' (what pymatgen's get_neighbor_list hands amof.coordination):
+ *   dist   = sqrt(d2) of P3
+ *   shifts = the integer image S with D = p_j - p_i + S.cell for the ORIGINAL (unwrapped) positions, recovered from the
+ *            wrapped-image vector dv of P3 as round(((dv - (p_j - p_i)) . inv)) -- an integer up to rounding noise. */
 typedef struct {
     const uint8_t *spec; int nspec; const double *cutoff; int64_t capacity, count; int32_t *pi, *pj;
+    const double *pos; double inv[9]; double *dist; int32_t *shifts;
 } nl_ctx;
 
 static void nl_cb(void *vctx, int i, int j, const double *dv, double d2) {
-    (void)dv;
     nl_ctx *c = (nl_ctx *)vctx;
     double cut = c->cutoff[c->spec[i] * c->nspec + c->spec[j]];
     if (cut > 0.0 && sqrt(d2) < cut) {
-        if (c->count < c->capacity) { c->pi[c->count] = i; c->pj[c->count] = j; }
+        if (c->count < c->capacity) {
+            c->pi[c->count] = i; c->pj[c->count] = j;
+            if (c->dist) c->dist[c->count] = sqrt(d2);
+            if (c->shifts) {
+                double t[3];
+                for (int k = 0; k < 3; ++k) t[k] = dv[k] - (c->pos[3 * j + k] - c->pos[3 * i + k]);
+                for (int k = 0; k < 3; ++k)
+                    c->shifts[3 * c->count + k] = (int32_t)lround((t[0] * c->inv[0 + k] + t[1] * c->inv[3 + k]) + t[2] * c->inv[6 + k]);
+            }
+        }
         c->count += 1;
     }
 }
 
 int orc_neighbour_pairs(int n, const double *pos, const double *cell, const uint8_t *spec, int nspec,
-                        const double *cutoff, int method, int64_t capacity, int32_t *pi, int32_t *pj, int64_t *count) {
+                        const double *cutoff, int method, int64_t capacity, int32_t *pi, int32_t *pj,
+                        double *dist, int32_t *shifts, int64_t *count) {
     if (n < 0 || nspec < 1 || !count) return ORC_ERR_ARG;
     *count = 0;
     double rc = max_cutoff(cutoff, nspec);
     if (!(rc > 0.0)) return ORC_OK;
-    nl_ctx c = {spec, nspec, cutoff, capacity, 0, pi, pj};
+    nl_ctx c;
+    memset(&c, 0, sizeof c);
+    c.spec = spec; c.nspec = nspec; c.cutoff = cutoff; c.capacity = capacity; c.pi = pi; c.pj = pj;
+    c.pos = pos; c.dist = dist; c.shifts = shifts;
+    int r0 = orc_cell_inverse(cell, c.inv);
+    if (r0) return r0;
     int r = visit_pairs(method, n, pos, cell, rc, nl_cb, &c);
     *count = c.count;
     return r;

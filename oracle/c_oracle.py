@@ -34,7 +34,7 @@ def lib():
         L.orc_cn_frame.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, _u64p]
         L.orc_cn_traj.argtypes = [C.c_int, C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, _u64p]
         L.orc_neighbour_pairs.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int64, C.POINTER(C.c_int32),
-                                          C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+                                          C.POINTER(C.c_int32), _dp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.orc_bad_frame.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.c_int, C.c_int, _u64p, _u64p]
         L.orc_bad_angles.argtypes = [C.c_int, _dp, _dp, _u8p, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_long]
@@ -104,22 +104,28 @@ def cn_traj(pos, cell, spec, nspec, cutoff, method=1, threads=1):
     return counts
 
 
-def neighbour_pairs(pos, cell, spec, nspec, cutoff, method=1):
+def neighbour_pairs(pos, cell, spec, nspec, cutoff, method=1, quantities=False):
     """One frame -> directed neighbour pairs (i, j) as ase.neighbor_list('ij', ...) would list them (amof/atom.py:82),
-    sorted by (i, j); a pair appears once per periodic image under the cutoff."""
+    sorted by (i, j, S); a pair appears once per periodic image under the cutoff.  With ``quantities`` also the
+    distances and the integer image shifts S (D = p_j - p_i + S.cell) of ase's 'd' and 'S'."""
     pos, pp = _d(pos); cell, cp = _d(cell); cutoff, kp = _d(cutoff)
     spec = np.ascontiguousarray(spec, dtype=np.uint8)
     n = pos.shape[0]
     count = C.c_int64(0)
     i32p = C.POINTER(C.c_int32)
-    _check(lib().orc_neighbour_pairs(n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, 0, None, None, C.byref(count)),
-           "neighbour_pairs")
+    _check(lib().orc_neighbour_pairs(n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, 0, None, None, None, None,
+                                     C.byref(count)), "neighbour_pairs")
     pi = np.zeros(count.value, dtype=np.int32)
     pj = np.zeros(count.value, dtype=np.int32)
+    dist = np.zeros(count.value, dtype=np.float64)
+    shifts = np.zeros((count.value, 3), dtype=np.int32)
     if count.value:
         _check(lib().orc_neighbour_pairs(n, pp, cp, spec.ctypes.data_as(_u8p), nspec, kp, method, count.value,
-                                         pi.ctypes.data_as(i32p), pj.ctypes.data_as(i32p), C.byref(count)), "neighbour_pairs")
-    order = np.lexsort((pj, pi))
+                                         pi.ctypes.data_as(i32p), pj.ctypes.data_as(i32p), dist.ctypes.data_as(_dp),
+                                         shifts.ctypes.data_as(i32p), C.byref(count)), "neighbour_pairs")
+    order = np.lexsort((shifts[:, 2], shifts[:, 1], shifts[:, 0], pj, pi))
+    if quantities:
+        return pi[order], pj[order], dist[order], shifts[order]
     return pi[order], pj[order]
 
 

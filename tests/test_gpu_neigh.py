@@ -53,6 +53,26 @@ def test_random_boxes(backend, seed, n, tri, size):
     assert _rows(off, nbr) == want
 
 
+@pytest.mark.parametrize("seed,n,tri,size,scale", [(11, 250, True, 10.0, 1.0), (12, 40, True, 5.0, 2.2), (13, 60, False, 6.0, 1.6)])
+def test_distances_and_shifts(backend, seed, n, tri, size, scale):
+    """ase's 'd' and 'S' per pair: bit-exact distances, integer image shifts for the positions AS GIVEN (they spill
+    outside the cell on purpose), rows ordered by (j, S); D = p_j - p_i + S.cell reproduces the distance."""
+    S = 3
+    pos, cell, spec = random_box(seed, n, S, tri, size, scale_pos=3.0)
+    cut = np.array([[2.6, 3.0, 0.0], [3.0, 0.0, 2.8], [0.0, 2.8, 2.4]]) * scale
+    off, nbr, dist, shifts = backend.neighbour_list(spec, S, pos, cell, cut, quantities=True)
+    wi, wj, wd, ws = orc.neighbour_pairs(pos, cell, spec, S, cut, quantities=True)
+    owner = np.repeat(np.arange(n), np.diff(off))
+    assert len(nbr) == len(wi) > 50
+    assert np.array_equal(owner, wi) and np.array_equal(nbr, wj)
+    assert np.array_equal(shifts, ws)
+    assert np.array_equal(dist, wd)                              # same d2 (P3), IEEE sqrt on both sides
+    D = pos[nbr] - pos[owner] + shifts @ cell
+    np.testing.assert_allclose(np.linalg.norm(D, axis=1), dist, rtol=0, atol=1e-12)
+    lim = cut[spec[owner], spec[nbr]]
+    assert np.all(dist < lim)
+
+
 def test_counts_match_the_fused_cn_analysis(backend):
     """the list and the fused counting kernel see the same pairs"""
     S = 3

@@ -95,6 +95,24 @@ def test_neighbour_list_images_and_twin():
             assert len(i) > 20 and np.array_equal(i, i2[o]) and np.array_equal(j, j2[o])
 
 
+def test_neighbour_list_distances_and_shifts():
+    """ase's 'd' and 'S': for one atom in a unit cube the 6 neighbours at cutoff 1.1 are its own images S = +-e_k at
+    distance exactly 1; on random boxes with positions outside the cell, D = p_j - p_i + S.cell reproduces d and both
+    enumerations return the same (i, j, S, d)."""
+    pos = np.array([[2.3, -0.6, 0.5]])                        # outside the cell on purpose
+    i, j, d, S = orc.neighbour_pairs(pos, np.eye(3), np.zeros(1, dtype=np.uint8), 1, np.array([[1.1]]), quantities=True)
+    assert sorted(map(tuple, S.tolist())) == sorted([(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)])
+    assert np.all(d == 1.0)
+    cut = np.array([[2.6, 3.0, 0.0], [3.0, 0.0, 2.8], [0.0, 2.8, 2.4]]) * 1.5
+    p, cell, sp = random_box(8, 80, 3, True, 6.0, scale_pos=3.0)
+    a = orc.neighbour_pairs(p, cell, sp, 3, cut, method=0, quantities=True)
+    b = orc.neighbour_pairs(p, cell, sp, 3, cut, method=1, quantities=True)
+    assert len(a[0]) > 200 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    i, j, d, S = a
+    np.testing.assert_allclose(np.linalg.norm(p[j] - p[i] + S @ cell, axis=1), d, rtol=0, atol=1e-12)
+    assert np.abs(S).max() >= 2                               # positions spill over several cells: S absorbs it
+
+
 def test_zif4_bad_golden(zif4):
     g = GOLD["bad_N_Zn_N@2.5"]
     cut = np.zeros((4, 4))
