@@ -554,6 +554,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     off = (off + 15) & ~(size_t)15;
     FlatRun *s_runs = reinterpret_cast<FlatRun *>(smem_raw + off);         off += sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32);
     uint16_t *s_key = reinterpret_cast<uint16_t *>(smem_raw + off);
+    (void)s_runs;                                  // only the flat-scan variant uses it
     SmemAddr sa;
     {
         const unsigned sb = opaque_u32((unsigned)__cvta_generic_to_shared(smem_raw));

@@ -135,10 +135,12 @@ def test_empty_and_errors(backend):
 
 
 @pytest.mark.parametrize("env", [{"AMOFB_PAIR_GENERIC": "1"}, {"AMOFB_PAIR_WARP": "1"}, {"AMOFB_PAIR_WARP": "1", "AMOFB_CELL_DIV": "1"}, {"AMOFB_TILE_CAP": "256"}, {"AMOFB_TILE_CAP": "300", "AMOFB_CELL_DIV": "1"},
-                                 {"AMOFB_CELL_DIV": "3"}, {"AMOFB_TILE_BLOCKS_PER_SM": "1"}])
+                                 {"AMOFB_CELL_DIV": "3"}, {"AMOFB_TILE_BLOCKS_PER_SM": "1"}, {"AMOFB_PAIR_PIPE": "1"},
+                                 {"AMOFB_PAIR_PIPE": "1", "AMOFB_TILE_CAP": "300"}, {"AMOFB_CN_NO_FILTER": "1"}])
 def test_kernel_variants_agree(backend, monkeypatch, env):
     """Generic kernel, tiled kernel with tiny staging capacity (row-split tiles and 'hard' cells handed to the
-    generic kernel), other cell sizes: all must give the oracle's integers."""
+    generic kernel), other cell sizes, the warp-streaming and the producer/consumer kernels: all must give the oracle's
+    integers."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     S = 3
