@@ -7,6 +7,7 @@
 #include "pair_warp.cuh"
 #include "pair_pipe.cuh"
 #include "neigh.cuh"
+#include "pair_list.cuh"
 #include "bad.cuh"
 #include "msd.cuh"
 
@@ -259,6 +260,7 @@ struct BatchSlot {
     SAtom *d_sorted = nullptr;
     uint32_t *d_orig = nullptr;            // only when the batcher was asked for it (want_orig)
     int *d_wraps = nullptr;                // idem: [frames][n_atoms][3]
+    uint32_t *d_slot = nullptr;            // only with want_slot: [frames][n_atoms] atom -> sorted position
     unsigned long long *d_out = nullptr, *h_out = nullptr;   // per-frame outputs of the batch
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     int frames = 0;        // frames of the batch in flight (0 = idle)
@@ -274,6 +276,7 @@ struct Batcher {
     uint8_t *d_species_keep = nullptr;   // optional species filter of the cell list (bond angles)
     int n_keep = 0;                      // atoms per frame that pass it (= n_atoms without a filter)
     bool want_orig = false;              // keep the original index of every sorted atom
+    bool want_slot = false;              // keep every atom's position in the sorted order
     BatchSlot slot[2];
     int next = 0;
     int64_t frames_seen = 0;
@@ -285,7 +288,7 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
     for (auto &s : b.slot) {
         pool_put(ctx, s.d_raw); pool_put(ctx, s.d_geom); pool_put(ctx, s.h_geom);
         pool_put(ctx, s.d_cell_count); pool_put(ctx, s.d_cell_start); pool_put(ctx, s.d_cid); pool_put(ctx, s.d_rank);
-        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_wraps); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
+        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_wraps); pool_put(ctx, s.d_slot); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
@@ -320,6 +323,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
         AMOFB_TRY(dev_alloc(ctx, &s.d_sorted, na));
         if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_orig, na));
         if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_wraps, na * 3));
+        if (b.want_slot) AMOFB_TRY(dev_alloc(ctx, &s.d_slot, na));
         if (per_frame_out > 0) {
             AMOFB_TRY(dev_alloc(ctx, &s.d_out, (size_t)b.cap_frames * per_frame_out));
             AMOFB_TRY(pinned_alloc(ctx, &s.h_out, (size_t)b.cap_frames * per_frame_out));
@@ -381,6 +385,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.species_keep = b.d_species_keep;
     pa.orig = s.d_orig;
     pa.wraps = s.d_wraps;
+    pa.slot = s.d_slot;
     long long total = (long long)nf * b.n_atoms;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;
@@ -445,6 +450,19 @@ struct PairState {
     // tiled path (pair_tiled.cuh)
     bool tiled = false, cn_wide = false;
     bool pipe = false;            // producer/consumer kernel (pair_pipe.cuh) instead of k_pair_tiled
+    // reused pair list (pair_list.cuh)
+    bool list_mode = false;
+    double list_skin = 0.0;
+    int list_seg = 0, list_cap = 0, list_max_tiles = 0;
+    SAtom *d_refsorted = nullptr;
+    int *d_ref_of = nullptr, *d_lflags = nullptr, *d_ntiles_ref = nullptr, *d_lcounts = nullptr;
+    unsigned char *d_isref = nullptr, *d_valid = nullptr;
+    unsigned *d_maxdisp2 = nullptr, *d_entries = nullptr;
+    PairTile *d_tiles_ref = nullptr;
+    int64_t list_frames = 0;
+    int *h_lflags = nullptr;          // pinned copy of d_lflags of the last list batch (capacity feedback, never waited for)
+    cudaEvent_t ev_lflags = nullptr;
+    bool lflags_pending = false;
     // fp32 fast path (pair_tiled.cuh): host-evaluated certainty bands
     bool f32_ok = false;
     F32Params f32{};
@@ -469,6 +487,10 @@ static void pair_release(amofb_ctx *ctx) {
     batcher_release(ctx, p->bt);
     pool_put(ctx, p->d_edge2); pool_put(ctx, p->d_cnthr2); pool_put(ctx, p->d_keyidx); pool_put(ctx, p->d_slabs); pool_put(ctx, p->d_hist);
     pool_put(ctx, p->d_tiles); pool_put(ctx, p->d_ntiles); pool_put(ctx, p->d_flags); pool_put(ctx, p->d_hard); pool_put(ctx, p->d_cn_band);
+    pool_put(ctx, p->d_refsorted); pool_put(ctx, p->d_ref_of); pool_put(ctx, p->d_lflags); pool_put(ctx, p->d_ntiles_ref); pool_put(ctx, p->d_lcounts);
+    pool_put(ctx, p->d_isref); pool_put(ctx, p->d_valid); pool_put(ctx, p->d_maxdisp2); pool_put(ctx, p->d_entries); pool_put(ctx, p->d_tiles_ref);
+    pool_put(ctx, p->h_lflags);
+    if (p->ev_lflags) cudaEventDestroy(p->ev_lflags);
     delete p;
     ctx->pair = nullptr;
 }
@@ -572,6 +594,16 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if (!(rcut > 0.0)) rcut = 1e-3;   // all cutoffs zero: nothing will be counted, any grid works
     int cell_div = env_int("AMOFB_CELL_DIV", p->has_rdf ? 2 : 1);
     if (cell_div < 1) cell_div = 1;
+    // reused pair list (pair_list.cuh): cells and stencils are sized for rc + skin, for every frame
+    if (p->has_rdf && env_int("AMOFB_PAIR_LIST", 0)) {
+        const char *sk = getenv("AMOFB_LIST_SKIN");
+        p->list_skin = sk ? atof(sk) : 2.0;
+        if (!(p->list_skin > 0.0) || !(p->list_skin < rcut)) p->list_skin = 2.0 < rcut ? 2.0 : 0.2 * rcut;
+        p->list_seg = std::max(2, env_int("AMOFB_LIST_SEG", 16));
+        p->list_mode = true;
+        p->bt.want_slot = true;
+        rcut += p->list_skin;
+    }
     if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, p->has_cn ? p->nkeys : 0))) return fail(rc);
     if (!p->has_rdf && !env_int("AMOFB_CN_NO_FILTER", 0)) {
         // counts only (amof.cn): a species without a positive cutoff towards any species can neither count nor be counted,
@@ -656,6 +688,13 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
             if (e1 == cudaSuccess && per_sm >= 1) {
                 p->tiled = true;
                 p->tile_grid = ctx->num_sms * per_sm;
+                if (p->list_mode && !want_pipe) {
+                    cudaError_t e2 = cudaFuncSetAttribute(k_list_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+                    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_list_scan<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+                    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_list_scan<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+                    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_list_scan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+                    if (e2 != cudaSuccess) { cudaGetLastError(); p->list_mode = false; }
+                } else p->list_mode = false;
                 // a tile has at least one home atom and usually ~100 (a column chunk); N/2 + 1024 per frame is ample, and an
                 // overflow is detected and reported (d_flags) rather than silently dropped
                 p->max_tiles = (int)std::min<size_t>(std::min<size_t>(p->bt.cells_per_frame, (size_t)n_atoms / 2 + 1024) * p->bt.cap_frames,
@@ -803,12 +842,92 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 else zlen_max = std::min(zlen_max, (int)room);
             }
             if (!f32_now) zlen_max = TILE_MAX_ZLEN;
+            // reused pair list: every frame of the batch must have the cell of the first one, and the lists must fit
+            bool list_now = tiled && p->list_mode && !p->pipe && !f32_now && nf >= 2;
+            for (int f = 1; f < nf && list_now; ++f)
+                if (memcmp(s->h_geom[f].cell, s->h_geom[0].cell, sizeof(double) * 9) != 0) list_now = false;
+            ListArgs la;
+            if (list_now) {
+                const FrameGeom &g0 = s->h_geom[0];
+                const int K = p->list_seg;
+                const int n_ref = (nf + K - 1) / K;
+                const long long tiles_ref = (long long)n_ref * g0.nc[0] * g0.nc[1] * 2;       // up to two tiles per column, else the segment falls back
+                const double rl = sqrt(p->r2search) + p->list_skin;
+                const double vol = host_cell_volume(g0.cell);
+                const double per_home = 0.5 * 4.18879 * rl * rl * rl * (double)b.n_atoms / std::max(vol, 1e-30);
+                const double homes = (double)b.n_atoms / std::max(1.0, (double)g0.nc[0] * g0.nc[1]);
+                long long cap = (long long)(2.5 * per_home * homes) + 4096;
+                // feedback from an earlier batch whose largest list did not fit (read only if its copy has landed)
+                if (p->lflags_pending && cudaEventQuery(p->ev_lflags) == cudaSuccess) {
+                    p->lflags_pending = false;
+                    if (p->h_lflags[1] > p->list_cap) cap = std::max<long long>(cap, (long long)(1.3 * p->h_lflags[1]) + 1024);
+                }
+                if (tiles_ref > p->list_max_tiles || cap > p->list_cap) {      // (re)allocate: sizes only grow
+                    pool_put(ctx, p->d_entries); pool_put(ctx, p->d_lcounts); pool_put(ctx, p->d_tiles_ref);
+                    p->d_entries = nullptr; p->d_lcounts = nullptr; p->d_tiles_ref = nullptr;
+                    p->list_max_tiles = (int)std::max<long long>(tiles_ref, p->list_max_tiles);
+                    p->list_cap = (int)std::max<long long>(cap, p->list_cap);
+                    if ((size_t)p->list_max_tiles * (size_t)p->list_cap > ((size_t)6 << 30) / sizeof(unsigned)) list_now = false;   // > 6 GB of lists: not worth it
+                    else {
+                        AMOFB_TRY(dev_alloc(ctx, &p->d_entries, (size_t)p->list_max_tiles * p->list_cap));
+                        AMOFB_TRY(dev_alloc(ctx, &p->d_lcounts, (size_t)p->list_max_tiles));
+                        AMOFB_TRY(dev_alloc(ctx, &p->d_tiles_ref, (size_t)p->list_max_tiles));
+                    }
+                }
+            }
+            if (list_now) {
+                const int K = p->list_seg;
+                if (!p->d_refsorted) {
+                    const size_t cf = (size_t)b.cap_frames;
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_refsorted, cf * b.n_atoms));
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_ref_of, cf));
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_isref, cf));
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_valid, cf));
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_maxdisp2, cf));
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_lflags, 4));
+                    AMOFB_TRY(dev_alloc(ctx, &p->d_ntiles_ref, 4));
+                    AMOFB_TRY(pinned_alloc(ctx, &p->h_lflags, 4));
+                    CUDA_TRY(ctx, cudaEventCreateWithFlags(&p->ev_lflags, cudaEventDisableTiming));
+                }
+                std::vector<int> ref_of((size_t)nf);
+                std::vector<unsigned char> isref((size_t)nf);
+                for (int f = 0; f < nf; ++f) { ref_of[f] = (f / K) * K; isref[f] = (f % K) == 0; }
+                CUDA_TRY(ctx, cudaMemcpyAsync(p->d_ref_of, ref_of.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, ctx->s_compute));     // pageable: staged before return
+                CUDA_TRY(ctx, cudaMemcpyAsync(p->d_isref, isref.data(), (size_t)nf, cudaMemcpyHostToDevice, ctx->s_compute));
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_maxdisp2, 0, sizeof(unsigned) * nf, ctx->s_compute));
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_lflags, 0, sizeof(int) * 4, ctx->s_compute));
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles_ref, 0, sizeof(int) * 4, ctx->s_compute));
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_hard, 0, ncell_total, ctx->s_compute));
+                RegroupArgs ra;
+                ra.sorted = s->d_sorted; ra.slot = s->d_slot; ra.geom = s->d_geom; ra.ref_of = p->d_ref_of; ra.refsorted = p->d_refsorted;
+                ra.maxdisp2 = p->d_maxdisp2; ra.n_atoms = b.n_atoms; ra.n_frames = nf;
+                k_regroup<<<(unsigned)std::min<long long>(((long long)nf * b.n_atoms + 255) / 256, (long long)ctx->num_sms * 16), 256, 0, ctx->s_compute>>>(ra);
+                PlanArgs plr;
+                plr.geom = s->d_geom; plr.cell_start = s->d_cell_start; plr.tiles = p->d_tiles_ref; plr.n_tiles = p->d_ntiles_ref;
+                plr.flags = p->d_lflags; plr.hard = p->d_hard; plr.n_frames = nf; plr.cap = p->tile_cap; plr.max_tiles = p->list_max_tiles; plr.zlen_max = zlen_max;
+                plr.sel = p->d_isref; plr.want = 1;
+                k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(plr);
+                la.t.p = a; la.t.f = p->f32; la.t.f.enabled = 0; la.t.tiles = p->d_tiles_ref; la.t.n_tiles = p->d_ntiles_ref; la.t.cap = p->tile_cap;
+                la.t.max_tiles = p->list_max_tiles; la.t.p.hard_mask = nullptr; la.t.p.n_hard = nullptr;
+                la.refsorted = p->d_refsorted; la.ref_of = p->d_ref_of; la.valid = p->d_valid; la.entries = p->d_entries; la.counts = p->d_lcounts;
+                la.flags = p->d_lflags; la.list_cap = p->list_cap; la.seg_len = K;
+                {
+                    const double rl = sqrt(p->r2search) + p->list_skin;
+                    la.r2list = rl * rl * (1.0 + 1e-9);
+                }
+                k_list_build<<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(la);
+                const float lim = (float)(0.5 * p->list_skin * (1.0 - 1e-6));
+                k_list_mask<<<(nf + 127) / 128, 128, 0, ctx->s_compute>>>(p->d_maxdisp2, p->d_lflags, p->d_ntiles_ref, lim * lim, nf, p->d_valid);
+                ctx->launches += 4;
+                CUDA_TRY(ctx, cudaGetLastError());
+            }
             if (tiled) {
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles, 0, sizeof(int) * 4, ctx->s_compute));
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_hard, 0, ncell_total, ctx->s_compute));
                 PlanArgs pl;
                 pl.geom = s->d_geom; pl.cell_start = s->d_cell_start; pl.tiles = p->d_tiles; pl.n_tiles = p->d_ntiles;
                 pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles; pl.zlen_max = zlen_max;
+                pl.sel = list_now ? p->d_valid : nullptr; pl.want = 0;       // with a list: only the frames it cannot serve
                 k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(pl);      // one warp per column
                 TiledArgs ta;
                 ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;
@@ -833,6 +952,32 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
             else pair_launch<false, true, false>(ctx, p, a, grid);
             ctx->launches += 1;
             CUDA_TRY(ctx, cudaGetLastError());
+            if (list_now) {
+                la.t.p = a; la.t.p.hard_mask = nullptr; la.t.p.n_hard = nullptr;
+                void *kargs[] = {(void *)&la};
+                const void *kfn = !p->has_cn ? (const void *)k_list_scan<false, false>
+                                             : (p->cn_wide ? (const void *)k_list_scan<true, true> : (const void *)k_list_scan<true, false>);
+                CUDA_TRY(ctx, cudaLaunchKernel(kfn, dim3(p->tile_grid), dim3(TILE_THREADS), kargs, p->tile_smem, ctx->s_compute));
+                ctx->launches += 1;
+                p->list_frames += nf;
+                if (!p->lflags_pending) {
+                    CUDA_TRY(ctx, cudaMemcpyAsync(p->h_lflags, p->d_lflags, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->s_compute));
+                    CUDA_TRY(ctx, cudaEventRecord(p->ev_lflags, ctx->s_compute));
+                    p->lflags_pending = true;
+                }
+                if (env_int("AMOFB_LIST_DEBUG", 0)) {          // how many frames the list really served (synchronises: debugging only)
+                    std::vector<unsigned char> v((size_t)nf);
+                    int fl[4] = {0, 0, 0, 0}, nt[4] = {0, 0, 0, 0};
+                    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+                    CUDA_TRY(ctx, cudaMemcpy(v.data(), p->d_valid, (size_t)nf, cudaMemcpyDeviceToHost));
+                    CUDA_TRY(ctx, cudaMemcpy(fl, p->d_lflags, sizeof fl, cudaMemcpyDeviceToHost));
+                    CUDA_TRY(ctx, cudaMemcpy(nt, p->d_ntiles_ref, sizeof nt, cudaMemcpyDeviceToHost));
+                    int nv = 0;
+                    for (unsigned char x : v) nv += x;
+                    fprintf(stderr, "[amofb list] batch of %d frames: %d served by the list, flags %d (largest list %d), reference tiles %d of %d (hard %d), cap %d entries\n",
+                            nf, nv, fl[0], fl[1], nt[0], p->list_max_tiles, nt[1], p->list_cap);
+                }
+            }
             if (ctx->profiling) {
                 CUDA_TRY(ctx, cudaEventRecord(e1, ctx->s_compute));
                 ctx->pending_pair_events.emplace_back(e0, e1);

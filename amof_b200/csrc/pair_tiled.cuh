@@ -57,6 +57,8 @@ struct PlanArgs {
     uint8_t *hard;           // batch-wide per-cell mask
     int n_frames, cap, max_tiles;
     int zlen_max;            // <= TILE_MAX_ZLEN; smaller when the fp32 path bounds the tile extent
+    const unsigned char *sel;   // optional per-frame selector: only frames with sel[f] == want are planned
+    int want;
 };
 
 __device__ __forceinline__ int tile_rows(const FrameGeom &g) { return (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1); }
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
     int f = 0;
     // frames may have different grids: walk the frames (n_frames is small next to the thread count)
     for (; f < a.n_frames; ++f) {
-        long long cols = (long long)a.geom[f].nc[0] * a.geom[f].nc[1];
+        long long cols = (a.sel && a.sel[f] != (unsigned char)a.want) ? 0 : (long long)a.geom[f].nc[0] * a.geom[f].nc[1];
         if (t < cols) break;
         t -= cols;
     }

@@ -39,6 +39,7 @@ struct PrepArgs {
     const uint8_t *species_keep;   // [n_species] or nullptr
     uint32_t *orig;                // optional [F*N]: original atom index of every sorted atom (explicit neighbour lists)
     int *wraps;                    // optional [F*N][3]: cell translations removed from every sorted atom by P2
+    uint32_t *slot;                // optional [F*N]: position of every atom in its frame's sorted order (pair lists)
 };
 
 // wn (optional): the integer cell translations w_k = floor(f_k) that P2 removed
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
         if (a.orig) a.orig[(long long)f * a.n_atoms + dst] = (uint32_t)i;
+        if (a.slot) a.slot[idx] = dst;
         if (a.wraps) {
             int *wp = a.wraps + 3 * ((long long)f * a.n_atoms + dst);
             wp[0] = wn[0]; wp[1] = wn[1]; wp[2] = wn[2];
