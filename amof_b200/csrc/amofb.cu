@@ -851,7 +851,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 const FrameGeom &g0 = s->h_geom[0];
                 const int K = p->list_seg;
                 const int n_ref = (nf + K - 1) / K;
-                const long long tiles_ref = (long long)n_ref * g0.nc[0] * g0.nc[1] * 2;       // up to two tiles per column, else the segment falls back
+                const long long tiles_ref = (long long)n_ref * g0.nc[0] * g0.nc[1] * std::min(4, g0.nc[2]);   // up to four tiles per column, else the batch falls back
                 const double rl = sqrt(p->r2search) + p->list_skin;
                 const double vol = host_cell_volume(g0.cell);
                 const double per_home = 0.5 * 4.18879 * rl * rl * rl * (double)b.n_atoms / std::max(vol, 1e-30);
@@ -901,7 +901,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 RegroupArgs ra;
                 ra.sorted = s->d_sorted; ra.slot = s->d_slot; ra.geom = s->d_geom; ra.ref_of = p->d_ref_of; ra.refsorted = p->d_refsorted;
                 ra.maxdisp2 = p->d_maxdisp2; ra.n_atoms = b.n_atoms; ra.n_frames = nf;
-                k_regroup<<<(unsigned)std::min<long long>(((long long)nf * b.n_atoms + 255) / 256, (long long)ctx->num_sms * 16), 256, 0, ctx->s_compute>>>(ra);
+                k_regroup<<<(unsigned)std::min<long long>(((long long)nf * b.n_atoms + 255) / 256, (long long)ctx->num_sms * 64), 256, 0, ctx->s_compute>>>(ra);
                 PlanArgs plr;
                 plr.geom = s->d_geom; plr.cell_start = s->d_cell_start; plr.tiles = p->d_tiles_ref; plr.n_tiles = p->d_ntiles_ref;
                 plr.flags = p->d_lflags; plr.hard = p->d_hard; plr.n_frames = nf; plr.cap = p->tile_cap; plr.max_tiles = p->list_max_tiles; plr.zlen_max = zlen_max;

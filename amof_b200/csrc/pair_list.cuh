@@ -265,7 +265,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_list_build(Li
                         const double dx = (ox - me.x) + Tx, dy = (oy - me.y) + Ty, dz = (oz - me.z) + Tz;
                         const double dd = (dx * dx + dy * dy) + dz * dz;
                         if (dd < la.r2list && j > jskip) {
-                            const unsigned pos = atomicAdd(&s_count, 1u);
+                            // one shared-memory atomic per group of hitting lanes, not per hit
+                            const unsigned act = __activemask();
+                            const int leader = __ffs(act) - 1;
+                            unsigned base = 0;
+                            if (lane == leader) base = atomicAdd(&s_count, (unsigned)__popc(act));
+                            base = __shfl_sync(act, base, leader);
+                            const unsigned pos = base + (unsigned)__popc(act & ((1u << lane) - 1u));
                             if (pos < (unsigned)la.list_cap) out[pos] = (unsigned)j | ((unsigned)hidx << 11) | (sid << 22);
                         }
                     }
@@ -346,10 +352,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_list_scan(Lis
         }
         list_stage(lt, s_geom, a.cell_start + s_geom.cs_off, la.refsorted + (long long)t * a.n_atoms, sm.atoms, sm.off, s_rowimg, mbar, tma_phase);
         const unsigned *ent = la.entries + (size_t)q * la.list_cap;
+        // the entry of the next trip is fetched (from L2) before this trip's pair is evaluated
+        unsigned en_next = (warp * 32 + lane) < count ? __ldg(ent + warp * 32 + lane) : 0u;
         for (int e0 = warp * 32; e0 < count; e0 += nwarp * 32) {
             const int e = e0 + lane;
+            const unsigned en = en_next;
+            const int e2 = e + nwarp * 32;
+            en_next = e2 < count ? __ldg(ent + e2) : 0u;
             if (e >= count) continue;
-            const unsigned en = __ldg(ent + e);
             const unsigned aj = sa.atoms + (en & 2047u) * 32u, ai = sa.atoms + ((en >> 11) & 2047u) * 32u;
             const unsigned sid = en >> 22;
             double xj, yj, zj, xi, yi, zi;
