@@ -30,9 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CN_SETS = {'Zn-N': 2.5, 'C-N': 1.728, 'C-C': 1.752}
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_pair_tiled launch (107 frames of C2), ncu --set full,
-# profiles/r01_k_pair_tiled_ncu_full_summary.txt: 56.23 MB + 0.98 MB (the kernel reads the 32-byte cell-sorted records)
-PAIR_TRAFFIC = {"c2": 57.21e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_pair_tiled launch over 107 frames of C2, ncu --set full,
+# profiles/r01_k_pair_tiled_ncu_full_summary.txt: 56.24 MB + 2.35 MB (the kernel reads the 32-byte cell-sorted records);
+# kept PER FRAME and scaled to the frames of a bench launch
+PAIR_TRAFFIC_PER_FRAME = {"c2": (56.24e6 + 2.35e6) / 107.0}
 FP64_NOFMA_GOPS = 18515.3      # measured on this pool's B200 with tools/microbench.cu (gpurun_out/microbench.json)
 
 
@@ -423,7 +424,7 @@ def run_ours(args):
         pairs = u["pair_evals_per_step"] * args.steps
         fp64 = 10.0 * pairs / (k_ms / 1e3) / 1e9
         out["roofline"] = {"bound": "hbm", "kernel": "k_pair_tiled (+ k_pair_plan)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                           "traffic": PAIR_TRAFFIC.get(wl.name), "peak_source": how, "kernel_ms_per_launch": per_launch_ms, "launches": int(k_n),
+                           "traffic": (PAIR_TRAFFIC_PER_FRAME[wl.name] * frames_per_launch if wl.name in PAIR_TRAFFIC_PER_FRAME else None), "peak_source": how, "kernel_ms_per_launch": per_launch_ms, "launches": int(k_n),
                            "algorithmic_bytes_per_launch": wl.algorithmic_bytes_per_frame() * frames_per_launch,
                            "kernel_share_of_step": k_ms / dev_ms,
                            "note": "compute-bound kernel: ~130 in-range pairs per 24 B read, so the HBM fraction is small by design; "
