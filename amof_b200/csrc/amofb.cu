@@ -804,6 +804,9 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
             bool tiled = p->tiled;
             size_t ncell_total = 0;
             long long columns = 0;
+            int uniform_cols = nf > 0 ? s->h_geom[0].nc[0] * s->h_geom[0].nc[1] : 0;
+            for (int f = 0; f < nf; ++f)
+                if (s->h_geom[f].nc[0] * s->h_geom[f].nc[1] != uniform_cols) uniform_cols = 0;
             for (int f = 0; f < nf && tiled; ++f) {
                 const FrameGeom &g = s->h_geom[f];
                 int R = (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1);
@@ -905,7 +908,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 PlanArgs plr;
                 plr.geom = s->d_geom; plr.cell_start = s->d_cell_start; plr.tiles = p->d_tiles_ref; plr.n_tiles = p->d_ntiles_ref;
                 plr.flags = p->d_lflags; plr.hard = p->d_hard; plr.n_frames = nf; plr.cap = p->tile_cap; plr.max_tiles = p->list_max_tiles; plr.zlen_max = zlen_max;
-                plr.sel = p->d_isref; plr.want = 1;
+                plr.sel = p->d_isref; plr.want = 1; plr.uniform_cols = uniform_cols;
                 k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(plr);
                 la.t.p = a; la.t.f = p->f32; la.t.f.enabled = 0; la.t.tiles = p->d_tiles_ref; la.t.n_tiles = p->d_ntiles_ref; la.t.cap = p->tile_cap;
                 la.t.max_tiles = p->list_max_tiles; la.t.p.hard_mask = nullptr; la.t.p.n_hard = nullptr;
@@ -928,6 +931,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 pl.geom = s->d_geom; pl.cell_start = s->d_cell_start; pl.tiles = p->d_tiles; pl.n_tiles = p->d_ntiles;
                 pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles; pl.zlen_max = zlen_max;
                 pl.sel = list_now ? p->d_valid : nullptr; pl.want = 0;       // with a list: only the frames it cannot serve
+                pl.uniform_cols = uniform_cols;
                 k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(pl);      // one warp per column
                 TiledArgs ta;
                 ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;

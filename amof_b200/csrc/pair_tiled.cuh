@@ -59,6 +59,7 @@ struct PlanArgs {
     int zlen_max;            // <= TILE_MAX_ZLEN; smaller when the fp32 path bounds the tile extent
     const unsigned char *sel;   // optional per-frame selector: only frames with sel[f] == want are planned
     int want;
+    int uniform_cols;           // > 0: every frame has this many columns (nc0 * nc1), so frame = warp / uniform_cols
 };
 
 __device__ __forceinline__ int tile_rows(const FrameGeom &g) { return (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1); }
@@ -87,13 +88,21 @@ __global__ void __launch_bounds__(128) k_pair_plan(PlanArgs a) {
     const int lane = threadIdx.x & 31;
     long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int f = 0;
-    // frames may have different grids: walk the frames (n_frames is small next to the thread count)
-    for (; f < a.n_frames; ++f) {
-        long long cols = (a.sel && a.sel[f] != (unsigned char)a.want) ? 0 : (long long)a.geom[f].nc[0] * a.geom[f].nc[1];
-        if (t < cols) break;
-        t -= cols;
+    if (a.uniform_cols > 0) {
+        // the usual case (one cell for the whole batch): no walk over the frames
+        f = (int)(t / a.uniform_cols);
+        if (f >= a.n_frames) return;
+        t -= (long long)f * a.uniform_cols;
+        if (a.sel && a.sel[f] != (unsigned char)a.want) return;
+    } else {
+        // frames may have different grids: walk the frames
+        for (; f < a.n_frames; ++f) {
+            long long cols = (a.sel && a.sel[f] != (unsigned char)a.want) ? 0 : (long long)a.geom[f].nc[0] * a.geom[f].nc[1];
+            if (t < cols) break;
+            t -= cols;
+        }
+        if (f >= a.n_frames) return;
     }
-    if (f >= a.n_frames) return;
     const FrameGeom &g = a.geom[f];
     const uint32_t *cs = a.cell_start + g.cs_off;
     const int nc1 = g.nc[1], nc2 = g.nc[2], m2 = g.m[2];
