@@ -46,6 +46,15 @@ class OracleBackend:
                 nf += 1
         return hist, dropped, nf
 
+    def neighbour_list(self, species, n_species, positions, cell, cutoff, quantities=False):
+        species = np.asarray(species, dtype=np.uint8)
+        i, j, d, S = orc.neighbour_pairs(positions, cell, species, int(n_species), cutoff, quantities=True)
+        offsets = np.zeros(len(species) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(i, minlength=len(species)), out=offsets[1:])
+        if quantities:
+            return offsets, j.astype(np.int32), d, S
+        return offsets, j.astype(np.int32)
+
     def msd_open(self, n_frames, masses, species, n_species, cells):
         return _Session(int(n_frames), np.asarray(masses, dtype=np.float64), np.asarray(species, dtype=np.uint8),
                         int(n_species), np.asarray(cells, dtype=np.float64).reshape(int(n_frames), 3, 3))

@@ -295,3 +295,25 @@ def test_synthetic_configs_are_deterministic():
     assert len(n3) == 104448 and abs(c3[1, 0]) > 1 and abs(c3[2, 1]) > 1                 # sheared: triclinic
     r = synth.reduced_network("c4", 1)
     assert r.positions.shape == (1, 8640, 3)
+
+
+# ------------------------------------------------------------------------------------------------ neighbour list
+def test_get_neighborlist_host_logic(zif4):
+    """amof.atom.get_neighborlist (atom.py:72-87): a list with one list of neighbour indices per atom, built from the
+    cutoff dictionary in both key orders; the CSR form and the optional ase quantities 'd' and 'S' describe the same pairs."""
+    from amof_b200 import atom as amatom
+    cut = amatom.format_cutoff({'Zn-N': 2.5, 'C-N': 1.728})
+    nl = amatom.get_neighborlist(zif4, cut)
+    numbers = np.asarray(zif4.get_atomic_numbers())
+    assert isinstance(nl, list) and len(nl) == 272 and all(isinstance(r, list) for r in nl)
+    assert all(len(nl[i]) == 4 and all(numbers[j] == 7 for j in nl[i]) for i in np.where(numbers == 30)[0])
+    assert all(len(nl[i]) == 0 for i in np.where(numbers == 1)[0])                    # H is in no cutoff pair
+    assert all(i in nl[j] for i in range(272) for j in nl[i])                          # symmetric
+    assert all(r == sorted(r) for r in nl)
+    off, nbr, dist, shifts = amatom.get_neighborlist_csr(zif4, cut, quantities=True)
+    assert off[-1] == len(nbr) == sum(len(r) for r in nl) == 128 + 256
+    owner = np.repeat(np.arange(272), np.diff(off))
+    pos, cell = zif4.get_positions(), np.asarray(zif4.get_cell())
+    np.testing.assert_allclose(np.linalg.norm(pos[nbr] - pos[owner] + shifts @ cell, axis=1), dist, rtol=0, atol=1e-12)
+    lim = np.where((numbers[owner] == 30) | (numbers[nbr] == 30), 2.5, 1.728)
+    assert np.all(dist < lim)
