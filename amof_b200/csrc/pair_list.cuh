@@ -75,7 +75,19 @@ __global__ void __launch_bounds__(256) k_regroup(RegroupArgs a) {
         }
         out.s = (rt.s & 0xff) | ((long long)(m0 + 8) << 8) | ((long long)(m1 + 8) << 12) | ((long long)(m2 + 8) << 16);
         a.refsorted[(long long)t * a.n_atoms + posR] = out;
-        if (d2f > 0.f) atomicMax(&a.maxdisp2[t], __float_as_uint(d2f));
+        // one atomic per warp and frame: the lanes of a warp almost always share the frame
+        const unsigned act = __activemask();
+        bool warp_path = false;
+        if (act == 0xffffffffu) {
+            const int t0 = __shfl_sync(0xffffffffu, t, 0);
+            warp_path = __all_sync(0xffffffffu, t == t0);
+        }
+        if (warp_path) {
+            unsigned v = __float_as_uint(d2f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0 && v > 0u) atomicMax(&a.maxdisp2[t], v);
+        } else if (d2f > 0.f) atomicMax(&a.maxdisp2[t], __float_as_uint(d2f));
     }
 }
 
@@ -183,7 +195,7 @@ __device__ __forceinline__ ListSmem list_carve(unsigned char *smem_raw, const Ti
     m.cn = reinterpret_cast<uint32_t *>(smem_raw + off);      off += sizeof(uint32_t) * (size_t)(has_cn ? a.nkeys : 0);
     m.off = reinterpret_cast<int *>(smem_raw + off);          off += sizeof(int) * TILE_OFF_WORDS;
     off = (off + 15) & ~(size_t)15;
-    m.ttab = reinterpret_cast<double *>(smem_raw + off);      off += sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32);   // 4.5 KB >= 64 * 24 B
+    m.ttab = reinterpret_cast<double *>(smem_raw + off);      off += sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32);   // 4.5 KB >= 64 * 32 B
     m.key = reinterpret_cast<uint16_t *>(smem_raw + off);
     return m;
 }
@@ -346,9 +358,10 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_list_scan(Lis
             wrap_cell(lt.c0 + d0, s_geom.nc[0], s0_, q0_);
             wrap_cell(lt.c1 + d1, s_geom.nc[1], s1_, q1_);
             const double fs0 = (double)s0_, fs1 = (double)s1_, fs2 = (double)s2;
-            sm.ttab[3 * k] = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
-            sm.ttab[3 * k + 1] = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
-            sm.ttab[3 * k + 2] = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
+            sm.ttab[4 * k] = (fs0 * s_geom.cell[0] + fs1 * s_geom.cell[3]) + fs2 * s_geom.cell[6];
+            sm.ttab[4 * k + 1] = (fs0 * s_geom.cell[1] + fs1 * s_geom.cell[4]) + fs2 * s_geom.cell[7];
+            sm.ttab[4 * k + 2] = (fs0 * s_geom.cell[2] + fs1 * s_geom.cell[5]) + fs2 * s_geom.cell[8];
+            sm.ttab[4 * k + 3] = 0.0;
         }
         list_stage(lt, s_geom, a.cell_start + s_geom.cs_off, la.refsorted + (long long)t * a.n_atoms, sm.atoms, sm.off, s_rowimg, mbar, tma_phase);
         const unsigned *ent = la.entries + (size_t)q * la.list_cap;
@@ -362,15 +375,17 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_list_scan(Lis
             if (e >= count) continue;
             const unsigned aj = sa.atoms + (en & 2047u) * 32u, ai = sa.atoms + ((en >> 11) & 2047u) * 32u;
             const unsigned sid = en >> 22;
-            double xj, yj, zj, xi, yi, zi;
-            lds_xyz(aj, xj, yj, zj);
-            lds_xyz(ai, xi, yi, zi);
-            unsigned wj, wi;
-            asm("ld.shared.u32 %0, [%1+24];" : "=r"(wj) : "r"(aj));
-            asm("ld.shared.u32 %0, [%1+24];" : "=r"(wi) : "r"(ai));
+            double xj, yj, zj, xi, yi, zi, sjd, sid_d;
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj), "=d"(yj) : "r"(aj));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(zj), "=d"(sjd) : "r"(aj));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi), "=d"(yi) : "r"(ai));
+            asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(zi), "=d"(sid_d) : "r"(ai));
+            const unsigned wj = (unsigned)__double_as_longlong(sjd), wi = (unsigned)__double_as_longlong(sid_d);
             double Tx, Ty, Tz;
             if ((wj >> 8) == (wi >> 8)) {                      // both atoms moved by the same lattice translation since R (almost always 0)
-                Tx = lds_f64(ttab_addr + sid * 24u); Ty = lds_f64(ttab_addr + sid * 24u + 8u); Tz = lds_f64(ttab_addr + sid * 24u + 16u);
+                double pad;
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(Tx), "=d"(Ty) : "r"(ttab_addr + sid * 32u));
+                asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(Tz), "=d"(pad) : "r"(ttab_addr + sid * 32u));
             } else {
                 // S_t = S_R - m_j + m_i, then T as P3 forms it
                 const int rr = (int)(sid / 3u);
