@@ -4,10 +4,7 @@
 #include "prep.cuh"
 #include "pair.cuh"
 #include "pair_tiled.cuh"
-#include "pair_warp.cuh"
-#include "pair_pipe.cuh"
 #include "neigh.cuh"
-#include "pair_list.cuh"
 #include "bad.cuh"
 #include "msd.cuh"
 
@@ -260,7 +257,6 @@ struct BatchSlot {
     SAtom *d_sorted = nullptr;
     uint32_t *d_orig = nullptr;            // only when the batcher was asked for it (want_orig)
     int *d_wraps = nullptr;                // idem: [frames][n_atoms][3]
-    uint32_t *d_slot = nullptr;            // only with want_slot: [frames][n_atoms] atom -> sorted position
     unsigned long long *d_out = nullptr, *h_out = nullptr;   // per-frame outputs of the batch
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     int frames = 0;        // frames of the batch in flight (0 = idle)
@@ -276,7 +272,6 @@ struct Batcher {
     uint8_t *d_species_keep = nullptr;   // optional species filter of the cell list (bond angles)
     int n_keep = 0;                      // atoms per frame that pass it (= n_atoms without a filter)
     bool want_orig = false;              // keep the original index of every sorted atom
-    bool want_slot = false;              // keep every atom's position in the sorted order
     BatchSlot slot[2];
     int next = 0;
     int64_t frames_seen = 0;
@@ -288,7 +283,7 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
     for (auto &s : b.slot) {
         pool_put(ctx, s.d_raw); pool_put(ctx, s.d_geom); pool_put(ctx, s.h_geom);
         pool_put(ctx, s.d_cell_count); pool_put(ctx, s.d_cell_start); pool_put(ctx, s.d_cid); pool_put(ctx, s.d_rank);
-        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_wraps); pool_put(ctx, s.d_slot); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
+        pool_put(ctx, s.d_sorted); pool_put(ctx, s.d_orig); pool_put(ctx, s.d_wraps); pool_put(ctx, s.d_out); pool_put(ctx, s.h_out);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
@@ -323,7 +318,6 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
         AMOFB_TRY(dev_alloc(ctx, &s.d_sorted, na));
         if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_orig, na));
         if (b.want_orig) AMOFB_TRY(dev_alloc(ctx, &s.d_wraps, na * 3));
-        if (b.want_slot) AMOFB_TRY(dev_alloc(ctx, &s.d_slot, na));
         if (per_frame_out > 0) {
             AMOFB_TRY(dev_alloc(ctx, &s.d_out, (size_t)b.cap_frames * per_frame_out));
             AMOFB_TRY(pinned_alloc(ctx, &s.h_out, (size_t)b.cap_frames * per_frame_out));
@@ -385,7 +379,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.species_keep = b.d_species_keep;
     pa.orig = s.d_orig;
     pa.wraps = s.d_wraps;
-    pa.slot = s.d_slot;
+    pa.slot = nullptr;
     long long total = (long long)nf * b.n_atoms;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;
@@ -449,34 +443,11 @@ struct PairState {
     double cn_r2max = 0.0;
     // tiled path (pair_tiled.cuh)
     bool tiled = false, cn_wide = false;
-    bool pipe = false;            // producer/consumer kernel (pair_pipe.cuh) instead of k_pair_tiled
-    // reused pair list (pair_list.cuh)
-    bool list_mode = false;
-    double list_skin = 0.0;
-    int list_seg = 0, list_cap = 0, list_max_tiles = 0;
-    SAtom *d_refsorted = nullptr;
-    int *d_ref_of = nullptr, *d_lflags = nullptr, *d_ntiles_ref = nullptr, *d_lcounts = nullptr;
-    unsigned char *d_isref = nullptr, *d_valid = nullptr;
-    unsigned *d_maxdisp2 = nullptr, *d_entries = nullptr;
-    PairTile *d_tiles_ref = nullptr;
-    int64_t list_frames = 0;
-    int *h_lflags = nullptr;          // pinned copy of d_lflags of the last list batch (capacity feedback, never waited for)
-    cudaEvent_t ev_lflags = nullptr;
-    bool lflags_pending = false;
-    // fp32 fast path (pair_tiled.cuh): host-evaluated certainty bands
-    bool f32_ok = false;
-    F32Params f32{};
-    float2 *d_cn_band = nullptr;
-    double f32_lmax = 128.0;
     PairTile *d_tiles = nullptr;
     int *d_ntiles = nullptr, *d_flags = nullptr;
     uint8_t *d_hard = nullptr;
     int tile_cap = 0, tile_grid = 0, max_tiles = 0;
     size_t tile_smem = 0, hard_bytes = 0;
-    // warp-streaming path (pair_warp.cuh)
-    bool warp_mode = false;
-    int warp_grid = 0;
-    size_t warp_smem = 0;
 };
 
 static void pair_release(amofb_ctx *ctx) {
@@ -486,24 +457,14 @@ static void pair_release(amofb_ctx *ctx) {
     cudaStreamSynchronize(ctx->s_compute);
     batcher_release(ctx, p->bt);
     pool_put(ctx, p->d_edge2); pool_put(ctx, p->d_cnthr2); pool_put(ctx, p->d_keyidx); pool_put(ctx, p->d_slabs); pool_put(ctx, p->d_hist);
-    pool_put(ctx, p->d_tiles); pool_put(ctx, p->d_ntiles); pool_put(ctx, p->d_flags); pool_put(ctx, p->d_hard); pool_put(ctx, p->d_cn_band);
-    pool_put(ctx, p->d_refsorted); pool_put(ctx, p->d_ref_of); pool_put(ctx, p->d_lflags); pool_put(ctx, p->d_ntiles_ref); pool_put(ctx, p->d_lcounts);
-    pool_put(ctx, p->d_isref); pool_put(ctx, p->d_valid); pool_put(ctx, p->d_maxdisp2); pool_put(ctx, p->d_entries); pool_put(ctx, p->d_tiles_ref);
-    pool_put(ctx, p->h_lflags);
-    if (p->ev_lflags) cudaEventDestroy(p->ev_lflags);
+    pool_put(ctx, p->d_tiles); pool_put(ctx, p->d_ntiles); pool_put(ctx, p->d_flags); pool_put(ctx, p->d_hard);
     delete p;
     ctx->pair = nullptr;
 }
 
-static const void *tiled_kernel(bool has_cn, bool cn_wide, bool f32) {
-    if (!has_cn) return f32 ? (const void *)k_pair_tiled<false, false, true> : (const void *)k_pair_tiled<false, false, false>;
-    if (cn_wide) return f32 ? (const void *)k_pair_tiled<true, true, true> : (const void *)k_pair_tiled<true, true, false>;
-    return f32 ? (const void *)k_pair_tiled<true, false, true> : (const void *)k_pair_tiled<true, false, false>;
-}
-
-static const void *pipe_kernel(bool has_cn, bool cn_wide) {
-    if (!has_cn) return (const void *)k_pair_pipe<false, false>;
-    return cn_wide ? (const void *)k_pair_pipe<true, true> : (const void *)k_pair_pipe<true, false>;
+static const void *tiled_kernel(bool has_cn, bool cn_wide) {
+    if (!has_cn) return (const void *)k_pair_tiled<false, false>;
+    return cn_wide ? (const void *)k_pair_tiled<true, true> : (const void *)k_pair_tiled<true, false>;
 }
 
 template <bool R, bool C, bool M>
@@ -594,16 +555,6 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if (!(rcut > 0.0)) rcut = 1e-3;   // all cutoffs zero: nothing will be counted, any grid works
     int cell_div = env_int("AMOFB_CELL_DIV", p->has_rdf ? 2 : 1);
     if (cell_div < 1) cell_div = 1;
-    // reused pair list (pair_list.cuh): cells and stencils are sized for rc + skin, for every frame
-    if (p->has_rdf && env_int("AMOFB_PAIR_LIST", 0)) {
-        const char *sk = getenv("AMOFB_LIST_SKIN");
-        p->list_skin = sk ? atof(sk) : 2.0;
-        if (!(p->list_skin > 0.0) || !(p->list_skin < rcut)) p->list_skin = 2.0 < rcut ? 2.0 : 0.2 * rcut;
-        p->list_seg = std::max(2, env_int("AMOFB_LIST_SEG", 16));
-        p->list_mode = true;
-        p->bt.want_slot = true;
-        rcut += p->list_skin;
-    }
     if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, p->has_cn ? p->nkeys : 0))) return fail(rc);
     if (!p->has_rdf && !env_int("AMOFB_CN_NO_FILTER", 0)) {
         // counts only (amof.cn): a species without a positive cutoff towards any species can neither count nor be counted,
@@ -641,60 +592,27 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     if (hist_n) cudaMemset(p->d_hist, 0, sizeof(unsigned long long) * hist_n);
     // tiled kernel: shared memory = fixed tables + as many staged atoms as still let two blocks share an SM
     if (p->smem_hist && n_atoms > 0 && p->bin_margin > 0.f && !env_int("AMOFB_PAIR_GENERIC", 0)) {
-        size_t fixed = smem_full + sizeof(int) * TILE_OFF_WORDS + (TILE_QUEUE ? sizeof(ulonglong2) * 64 * (TILE_THREADS / 32) : 0) +
-                       sizeof(FlatRun) * (FLAT_MAXE + 1) * (TILE_THREADS / 32) + 64;
-        int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", 2);
+        size_t fixed = smem_full + sizeof(int) * (TILE_OFF_WORDS + TILE_PRE_WORDS) + 64;
+        const size_t per_atom = sizeof(SAtom) + 1;                            // + the image code byte
+        int per_sm_target = env_int("AMOFB_TILE_BLOCKS_PER_SM", TILE_MIN_BLOCKS);
         size_t sm_total = (size_t)ctx->max_smem_optin + 1024;                 // 227 KB opt-in + 1 KB reserved per block
-        size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - 2048;     // driver reserve + the kernel's static shared memory
-        if (per_block > budget) per_block = budget;
-        // the fp32 fast path needs 16 more bytes per staged atom; it is only worth having when its margin is small
-        double f32_margin = 1.0;
-        {
-            const double u = 5.9604644775390625e-08, dmax = sqrt(std::max(p->r2search, 0.0)) * 1.001 + 1e-6;
-            const double ddiff = 2.0 * p->f32_lmax * u + u * dmax;
-            f32_margin = 2.0 * (sqrt(3.0) * ddiff + 2.0 * u * dmax) / (rmax / (double)nbins) + (double)nbins * 1.0e-6 + 2.0e-4;
-        }
-        const bool want_f32 = TILE_F32 && f32_margin <= 0.05 && !env_int("AMOFB_NO_F32", 0);
-        const size_t per_atom = sizeof(SAtom) + (want_f32 ? sizeof(float4) : 0);
-        fixed += want_f32 ? sizeof(float2) * p->nkeys : 0;
+        size_t per_block = sm_total / std::max(per_sm_target, 1) - 1024 - TILE_STATIC_SMEM;     // driver reserve + the kernel's static shared memory
+        if (per_block + TILE_STATIC_SMEM > (size_t)ctx->max_smem_optin) per_block = (size_t)ctx->max_smem_optin - TILE_STATIC_SMEM;
         long long cap = per_block > fixed ? (long long)((per_block - fixed) / per_atom) : 0;
-        // producer/consumer kernel: one block per SM, PIPE_STAGES tile buffers
-        const bool want_pipe = !want_f32 && env_int("AMOFB_PAIR_PIPE", 0) != 0;
-        if (want_pipe) {
-            const size_t pipe_fixed = pipe_layout(0, nbins, p->nkeys, S, p->has_cn).total;
-            const size_t pipe_budget = (size_t)ctx->max_smem_optin > 1024 ? (size_t)ctx->max_smem_optin - 1024 : 0;   // static: meta, mbarriers, counters
-            cap = pipe_budget > pipe_fixed ? (long long)((pipe_budget - pipe_fixed) / (sizeof(SAtom) * PIPE_STAGES)) : 0;
-        }
         int cap_env = env_int("AMOFB_TILE_CAP", 0);
         if (cap_env > 0 && cap_env < cap) cap = cap_env;
-        if (cap > 2000) cap = 2000;     // run lengths must stay below 2048 (magic-number divisions, 16-bit queue indices)
+        if (cap > 2000) cap = 2000;     // staged indices and flat candidate indices are packed into 16 bits each
         if (cap >= 256) {
             p->tile_cap = (int)cap;
-            p->tile_smem = want_pipe ? (size_t)pipe_layout((int)cap, nbins, p->nkeys, S, p->has_cn).total : fixed + per_atom * (size_t)cap;
+            p->tile_smem = fixed + per_atom * (size_t)cap;
             int per_sm = 0;
             p->cn_wide = p->has_cn && p->cn_r2max > p->r2max;
-            cudaError_t e1 = cudaSuccess;
-            if (want_pipe) {
-                const void *kfn = pipe_kernel(p->has_cn, p->cn_wide);
-                e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-                if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PIPE_THREADS, p->tile_smem);
-                if (e1 == cudaSuccess && per_sm >= 1) { p->pipe = true; per_sm = 1; }
-            }
-            for (int f32 = 0; f32 < 2 && e1 == cudaSuccess && !want_pipe; ++f32) {       // both flavours share the shared-memory size
-                const void *kfn = tiled_kernel(p->has_cn, p->cn_wide, f32 != 0);
-                e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-                if (e1 == cudaSuccess) { int n = 0; e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, TILE_THREADS, p->tile_smem); per_sm = f32 ? std::min(per_sm, n) : n; }
-            }
+            const void *kfn = tiled_kernel(p->has_cn, p->cn_wide);
+            cudaError_t e1 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
+            if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, TILE_THREADS, p->tile_smem);
             if (e1 == cudaSuccess && per_sm >= 1) {
                 p->tiled = true;
                 p->tile_grid = ctx->num_sms * per_sm;
-                if (p->list_mode && !want_pipe) {
-                    cudaError_t e2 = cudaFuncSetAttribute(k_list_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-                    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_list_scan<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-                    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_list_scan<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-                    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_list_scan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);
-                    if (e2 != cudaSuccess) { cudaGetLastError(); p->list_mode = false; }
-                } else p->list_mode = false;
                 // a tile has at least one home atom and usually ~100 (a column chunk); N/2 + 1024 per frame is ample, and an
                 // overflow is detected and reported (d_flags) rather than silently dropped
                 p->max_tiles = (int)std::min<size_t>(std::min<size_t>(p->bt.cells_per_frame, (size_t)n_atoms / 2 + 1024) * p->bt.cap_frames,
@@ -705,61 +623,11 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
                 if ((rc = dev_alloc(ctx, &p->d_flags, 1))) return fail(rc);
                 if ((rc = dev_alloc(ctx, &p->d_hard, p->hard_bytes))) return fail(rc);
                 cudaMemset(p->d_flags, 0, sizeof(int));
-#if TILE_F32
-                if (want_f32) {
-                    // error model of the fp32 path (see scan_run_f32), with a safety factor of 2 on the distance error
-                    const double u = 5.9604644775390625e-08;                    // 2^-24
-                    const double dmax = sqrt(std::max(p->r2search, 0.0)) * 1.001 + 1e-6;
-                    const double dcoord = p->f32_lmax * u;                      // one rounded local coordinate
-                    const double ddiff = 2.0 * dcoord + u * dmax;               // one coordinate difference
-                    auto E = [&](double d) { return 2.0 * (2.0 * sqrt(3.0) * d * ddiff * (1.0 + 4.0 * u) + 4.0 * u * d * d + 3.0 * ddiff * ddiff) + 1e-12; };
-                    auto fdown = [](double x) { float f = (float)x; while ((double)f > x) f = nextafterf(f, -INFINITY); return nextafterf(f, -INFINITY); };
-                    auto fup = [](double x) { float f = (float)x; while ((double)f < x) f = nextafterf(f, INFINITY); return nextafterf(f, INFINITY); };
-                    const double dr = rmax / (double)nbins;
-                    const double margin = 2.0 * (sqrt(3.0) * ddiff + 2.0 * u * dmax) / dr + (double)nbins * 1.0e-6 + 2.0e-4;
-                    if (margin <= 0.05) {
-                        F32Params &f = p->f32;
-                        const double rm = sqrt(p->r2max);
-                        f.r2max_lo = fdown(p->r2max - E(rm));
-                        f.r2max_hi = fup(p->r2max + E(rm));
-                        f.margin = (float)margin;
-                        std::vector<float2> band((size_t)p->nkeys, make_float2(0.f, 0.f));
-                        double cnhi = 0.0;
-                        for (int k = 0; k < p->nkeys; ++k)
-                            if (cnthr[k] > 0.0) {
-                                const double d = sqrt(cnthr[k]);
-                                band[k] = make_float2(fdown(cnthr[k] - E(d)), fup(cnthr[k] + E(d)));
-                                cnhi = std::max(cnhi, (double)band[k].y);
-                            }
-                        f.cn_hi = (float)cnhi;
-                        f.r2hi = std::max(f.r2max_hi, f.cn_hi);
-                        if ((rc = dev_alloc(ctx, &p->d_cn_band, band.size()))) return fail(rc);
-                        cudaMemcpy(p->d_cn_band, band.data(), sizeof(float2) * band.size(), cudaMemcpyHostToDevice);
-                        f.cn_band = p->d_cn_band;
-                        f.enabled = 1;
-                        p->f32_ok = true;
-                    }
-                }
-#endif
             } else cudaGetLastError();
         }
     }
-    if (p->smem_hist && n_atoms > 0 && p->bin_margin > 0.f && env_int("AMOFB_PAIR_WARP", 0)) {
-        p->warp_smem = smem_full + sizeof(SAtom) * 2 * WCHUNK * (WARP_THREADS / 32) + sizeof(uint32_t) * p->nkeys * (WARP_THREADS / 32) + 64;
-        int per_sm = 0;
-        cudaError_t e1 = p->has_cn
-            ? cudaFuncSetAttribute(k_pair_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->warp_smem)
-            : cudaFuncSetAttribute(k_pair_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->warp_smem);
-        if (e1 == cudaSuccess)
-            e1 = p->has_cn ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_warp<true>, WARP_THREADS, p->warp_smem)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_warp<false>, WARP_THREADS, p->warp_smem);
-        if (e1 == cudaSuccess && per_sm >= 1) {
-            p->warp_mode = true;
-            p->warp_grid = ctx->num_sms * per_sm;
-        } else cudaGetLastError();
-    }
     if (p->smem_hist) {
-        size_t nslab = (size_t)std::max(std::max(p->grid, p->tile_grid), p->warp_grid);
+        size_t nslab = (size_t)std::max(p->grid, p->tile_grid);
         if ((rc = dev_alloc(ctx, &p->d_slabs, hist_n * nslab))) return fail(rc);
         cudaMemset(p->d_slabs, 0, sizeof(unsigned long long) * hist_n * nslab);
     }
@@ -811,140 +679,25 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 const FrameGeom &g = s->h_geom[f];
                 int R = (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1);
                 if (R > TILE_MAX_ROWS || TILE_MAX_ENTRIES / R < 2 * g.m[2] + 1) tiled = false;
+                if (g.m[0] > g.nc[0] || g.m[1] > g.nc[1] || g.m[2] > g.nc[2]) tiled = false;     // image shifts beyond +-1 cell vector: generic kernel
                 ncell_total += (size_t)g.ncell + 1;
                 columns += (long long)g.nc[0] * g.nc[1];
-            }
-            if (p->warp_mode) {
-                WarpArgs wa;
-                wa.p = a; wa.total_cells = 0;
-                for (int f = 0; f < nf; ++f) wa.total_cells += s->h_geom[f].ncell;
-                if (p->has_cn) k_pair_warp<true><<<p->warp_grid, WARP_THREADS, p->warp_smem, ctx->s_compute>>>(wa);
-                else k_pair_warp<false><<<p->warp_grid, WARP_THREADS, p->warp_smem, ctx->s_compute>>>(wa);
-                ctx->launches += 1;
-                CUDA_TRY(ctx, cudaGetLastError());
-                if (ctx->profiling) {
-                    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->s_compute));
-                    ctx->pending_pair_events.emplace_back(e0, e1);
-                }
-                AMOFB_TRY(batcher_commit(ctx, b, *s, nf));
-                done += nf;
-                continue;
-            }
-            // fp32 path: local coordinates must stay below f32_lmax -> bound the tile length along the column
-            int zlen_max = TILE_MAX_ZLEN;
-            bool f32_now = tiled && p->f32_ok;
-            for (int f = 0; f < nf && f32_now; ++f) {
-                const FrameGeom &g = s->h_geom[f];
-                double e[3], ext = 0.0;
-                for (int k = 0; k < 3; ++k) {
-                    e[k] = sqrt((g.cell[3 * k] * g.cell[3 * k] + g.cell[3 * k + 1] * g.cell[3 * k + 1]) + g.cell[3 * k + 2] * g.cell[3 * k + 2]) / g.nc[k];
-                    ext += (g.m[k] + 2) * e[k];
-                }
-                const double room = (p->f32_lmax - ext) / e[2];
-                if (!(room >= 1.0)) f32_now = false;
-                else zlen_max = std::min(zlen_max, (int)room);
-            }
-            if (!f32_now) zlen_max = TILE_MAX_ZLEN;
-            // reused pair list: every frame of the batch must have the cell of the first one, and the lists must fit
-            bool list_now = tiled && p->list_mode && !p->pipe && !f32_now && nf >= 2;
-            for (int f = 1; f < nf && list_now; ++f)
-                if (memcmp(s->h_geom[f].cell, s->h_geom[0].cell, sizeof(double) * 9) != 0) list_now = false;
-            ListArgs la;
-            if (list_now) {
-                const FrameGeom &g0 = s->h_geom[0];
-                const int K = p->list_seg;
-                const int n_ref = (nf + K - 1) / K;
-                const long long tiles_ref = (long long)n_ref * g0.nc[0] * g0.nc[1] * std::min(4, g0.nc[2]);   // up to four tiles per column, else the batch falls back
-                const double rl = sqrt(p->r2search) + p->list_skin;
-                const double vol = host_cell_volume(g0.cell);
-                const double per_home = 0.5 * 4.18879 * rl * rl * rl * (double)b.n_atoms / std::max(vol, 1e-30);
-                const double homes = (double)b.n_atoms / std::max(1.0, (double)g0.nc[0] * g0.nc[1]);
-                long long cap = (long long)(2.5 * per_home * homes) + 4096;
-                // feedback from an earlier batch whose largest list did not fit (read only if its copy has landed)
-                if (p->lflags_pending && cudaEventQuery(p->ev_lflags) == cudaSuccess) {
-                    p->lflags_pending = false;
-                    if (p->h_lflags[1] > p->list_cap) cap = std::max<long long>(cap, (long long)(1.3 * p->h_lflags[1]) + 1024);
-                }
-                if (tiles_ref > p->list_max_tiles || cap > p->list_cap) {      // (re)allocate: sizes only grow
-                    pool_put(ctx, p->d_entries); pool_put(ctx, p->d_lcounts); pool_put(ctx, p->d_tiles_ref);
-                    p->d_entries = nullptr; p->d_lcounts = nullptr; p->d_tiles_ref = nullptr;
-                    p->list_max_tiles = (int)std::max<long long>(tiles_ref, p->list_max_tiles);
-                    p->list_cap = (int)std::max<long long>(cap, p->list_cap);
-                    if ((size_t)p->list_max_tiles * (size_t)p->list_cap > ((size_t)6 << 30) / sizeof(unsigned)) list_now = false;   // > 6 GB of lists: not worth it
-                    else {
-                        AMOFB_TRY(dev_alloc(ctx, &p->d_entries, (size_t)p->list_max_tiles * p->list_cap));
-                        AMOFB_TRY(dev_alloc(ctx, &p->d_lcounts, (size_t)p->list_max_tiles));
-                        AMOFB_TRY(dev_alloc(ctx, &p->d_tiles_ref, (size_t)p->list_max_tiles));
-                    }
-                }
-            }
-            if (list_now) {
-                const int K = p->list_seg;
-                if (!p->d_refsorted) {
-                    const size_t cf = (size_t)b.cap_frames;
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_refsorted, cf * b.n_atoms));
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_ref_of, cf));
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_isref, cf));
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_valid, cf));
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_maxdisp2, cf));
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_lflags, 4));
-                    AMOFB_TRY(dev_alloc(ctx, &p->d_ntiles_ref, 4));
-                    AMOFB_TRY(pinned_alloc(ctx, &p->h_lflags, 4));
-                    CUDA_TRY(ctx, cudaEventCreateWithFlags(&p->ev_lflags, cudaEventDisableTiming));
-                }
-                std::vector<int> ref_of((size_t)nf);
-                std::vector<unsigned char> isref((size_t)nf);
-                for (int f = 0; f < nf; ++f) { ref_of[f] = (f / K) * K; isref[f] = (f % K) == 0; }
-                CUDA_TRY(ctx, cudaMemcpyAsync(p->d_ref_of, ref_of.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, ctx->s_compute));     // pageable: staged before return
-                CUDA_TRY(ctx, cudaMemcpyAsync(p->d_isref, isref.data(), (size_t)nf, cudaMemcpyHostToDevice, ctx->s_compute));
-                CUDA_TRY(ctx, cudaMemsetAsync(p->d_maxdisp2, 0, sizeof(unsigned) * nf, ctx->s_compute));
-                CUDA_TRY(ctx, cudaMemsetAsync(p->d_lflags, 0, sizeof(int) * 4, ctx->s_compute));
-                CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles_ref, 0, sizeof(int) * 4, ctx->s_compute));
-                CUDA_TRY(ctx, cudaMemsetAsync(p->d_hard, 0, ncell_total, ctx->s_compute));
-                RegroupArgs ra;
-                ra.sorted = s->d_sorted; ra.slot = s->d_slot; ra.geom = s->d_geom; ra.ref_of = p->d_ref_of; ra.refsorted = p->d_refsorted;
-                ra.maxdisp2 = p->d_maxdisp2; ra.n_atoms = b.n_atoms; ra.n_frames = nf;
-                k_regroup<<<(unsigned)std::min<long long>(((long long)nf * b.n_atoms + 255) / 256, (long long)ctx->num_sms * 64), 256, 0, ctx->s_compute>>>(ra);
-                PlanArgs plr;
-                plr.geom = s->d_geom; plr.cell_start = s->d_cell_start; plr.tiles = p->d_tiles_ref; plr.n_tiles = p->d_ntiles_ref;
-                plr.flags = p->d_lflags; plr.hard = p->d_hard; plr.n_frames = nf; plr.cap = p->tile_cap; plr.max_tiles = p->list_max_tiles; plr.zlen_max = zlen_max;
-                plr.sel = p->d_isref; plr.want = 1; plr.uniform_cols = uniform_cols;
-                k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(plr);
-                la.t.p = a; la.t.f = p->f32; la.t.f.enabled = 0; la.t.tiles = p->d_tiles_ref; la.t.n_tiles = p->d_ntiles_ref; la.t.cap = p->tile_cap;
-                la.t.max_tiles = p->list_max_tiles; la.t.p.hard_mask = nullptr; la.t.p.n_hard = nullptr;
-                la.refsorted = p->d_refsorted; la.ref_of = p->d_ref_of; la.valid = p->d_valid; la.entries = p->d_entries; la.counts = p->d_lcounts;
-                la.flags = p->d_lflags; la.list_cap = p->list_cap; la.seg_len = K;
-                {
-                    const double rl = sqrt(p->r2search) + p->list_skin;
-                    la.r2list = rl * rl * (1.0 + 1e-9);
-                }
-                k_list_build<<<p->tile_grid, TILE_THREADS, p->tile_smem, ctx->s_compute>>>(la);
-                const float lim = (float)(0.5 * p->list_skin * (1.0 - 1e-6));
-                k_list_mask<<<(nf + 127) / 128, 128, 0, ctx->s_compute>>>(p->d_maxdisp2, p->d_lflags, p->d_ntiles_ref, lim * lim, nf, p->d_valid);
-                ctx->launches += 4;
-                CUDA_TRY(ctx, cudaGetLastError());
             }
             if (tiled) {
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_ntiles, 0, sizeof(int) * 4, ctx->s_compute));
                 CUDA_TRY(ctx, cudaMemsetAsync(p->d_hard, 0, ncell_total, ctx->s_compute));
                 PlanArgs pl;
                 pl.geom = s->d_geom; pl.cell_start = s->d_cell_start; pl.tiles = p->d_tiles; pl.n_tiles = p->d_ntiles;
-                pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles; pl.zlen_max = zlen_max;
-                pl.sel = list_now ? p->d_valid : nullptr; pl.want = 0;       // with a list: only the frames it cannot serve
+                pl.flags = p->d_flags; pl.hard = p->d_hard; pl.n_frames = nf; pl.cap = p->tile_cap; pl.max_tiles = p->max_tiles;
                 pl.uniform_cols = uniform_cols;
                 k_pair_plan<<<(unsigned)((columns + 3) / 4), 128, 0, ctx->s_compute>>>(pl);      // one warp per column
                 TiledArgs ta;
                 ta.p = a; ta.tiles = p->d_tiles; ta.n_tiles = p->d_ntiles; ta.cap = p->tile_cap; ta.max_tiles = p->max_tiles;
                 ta.p.hard_mask = nullptr; ta.p.n_hard = nullptr;
-                ta.f = p->f32; ta.f.enabled = f32_now ? 1 : 0;
                 {
                     void *kargs[] = {(void *)&ta};
-                    if (p->pipe)
-                        CUDA_TRY(ctx, cudaLaunchKernel(pipe_kernel(p->has_cn, p->cn_wide), dim3(p->tile_grid), dim3(PIPE_THREADS), kargs,
-                                                       p->tile_smem, ctx->s_compute));
-                    else
-                        CUDA_TRY(ctx, cudaLaunchKernel(tiled_kernel(p->has_cn, p->cn_wide, f32_now), dim3(p->tile_grid), dim3(TILE_THREADS), kargs,
-                                                       p->tile_smem, ctx->s_compute));
+                    CUDA_TRY(ctx, cudaLaunchKernel(tiled_kernel(p->has_cn, p->cn_wide), dim3(p->tile_grid), dim3(TILE_THREADS), kargs,
+                                                   p->tile_smem, ctx->s_compute));
                 }
                 ctx->launches += 2;
                 CUDA_TRY(ctx, cudaGetLastError());
@@ -956,32 +709,6 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
             else pair_launch<false, true, false>(ctx, p, a, grid);
             ctx->launches += 1;
             CUDA_TRY(ctx, cudaGetLastError());
-            if (list_now) {
-                la.t.p = a; la.t.p.hard_mask = nullptr; la.t.p.n_hard = nullptr;
-                void *kargs[] = {(void *)&la};
-                const void *kfn = !p->has_cn ? (const void *)k_list_scan<false, false>
-                                             : (p->cn_wide ? (const void *)k_list_scan<true, true> : (const void *)k_list_scan<true, false>);
-                CUDA_TRY(ctx, cudaLaunchKernel(kfn, dim3(p->tile_grid), dim3(TILE_THREADS), kargs, p->tile_smem, ctx->s_compute));
-                ctx->launches += 1;
-                p->list_frames += nf;
-                if (!p->lflags_pending) {
-                    CUDA_TRY(ctx, cudaMemcpyAsync(p->h_lflags, p->d_lflags, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->s_compute));
-                    CUDA_TRY(ctx, cudaEventRecord(p->ev_lflags, ctx->s_compute));
-                    p->lflags_pending = true;
-                }
-                if (env_int("AMOFB_LIST_DEBUG", 0)) {          // how many frames the list really served (synchronises: debugging only)
-                    std::vector<unsigned char> v((size_t)nf);
-                    int fl[4] = {0, 0, 0, 0}, nt[4] = {0, 0, 0, 0};
-                    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
-                    CUDA_TRY(ctx, cudaMemcpy(v.data(), p->d_valid, (size_t)nf, cudaMemcpyDeviceToHost));
-                    CUDA_TRY(ctx, cudaMemcpy(fl, p->d_lflags, sizeof fl, cudaMemcpyDeviceToHost));
-                    CUDA_TRY(ctx, cudaMemcpy(nt, p->d_ntiles_ref, sizeof nt, cudaMemcpyDeviceToHost));
-                    int nv = 0;
-                    for (unsigned char x : v) nv += x;
-                    fprintf(stderr, "[amofb list] batch of %d frames: %d served by the list, flags %d (largest list %d), reference tiles %d of %d (hard %d), cap %d entries\n",
-                            nf, nv, fl[0], fl[1], nt[0], p->list_max_tiles, nt[1], p->list_cap);
-                }
-            }
             if (ctx->profiling) {
                 CUDA_TRY(ctx, cudaEventRecord(e1, ctx->s_compute));
                 ctx->pending_pair_events.emplace_back(e0, e1);
@@ -1011,6 +738,13 @@ extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_co
         Batcher &b = p->bt;
         AMOFB_TRY(batcher_drain(ctx, b));
         const int S = p->n_species;
+        if (p->d_flags) {
+            // tile list overflow: some pairs were never evaluated, so NEITHER output may be handed out
+            int flags = 0;
+            CUDA_TRY(ctx, cudaMemcpyAsync(&flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
+            if (flags) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "tile list overflow (extremely inhomogeneous frame); rerun with AMOFB_PAIR_GENERIC=1");
+        }
         if (cn_counts) {
             if (!p->has_cn) return amofb_fail(ctx, AMOFB_ERR_ARG, "cn_counts requested but no cutoffs were given at begin");
             if (cn_frames != b.frames_seen)
@@ -1025,14 +759,8 @@ extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_co
         if (hist) {
             if (!p->has_rdf) return amofb_fail(ctx, AMOFB_ERR_ARG, "hist requested but nbins was 0 at begin");
             const size_t hist_n = (size_t)p->nkeys * p->nbins;
-            if (p->d_flags) {
-                int flags = 0;
-                CUDA_TRY(ctx, cudaMemcpyAsync(&flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
-                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_compute));
-                if (flags) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "tile list overflow (extremely inhomogeneous frame); rerun with AMOFB_PAIR_GENERIC=1");
-            }
             if (p->smem_hist) {
-                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, std::max(std::max(p->grid, p->tile_grid), p->warp_grid), (int)hist_n, p->d_hist);
+                k_slab_reduce<<<ctx->num_sms * 2, 256, 0, ctx->s_compute>>>(p->d_slabs, std::max(p->grid, p->tile_grid), (int)hist_n, p->d_hist);
                 ctx->launches += 1;
                 CUDA_TRY(ctx, cudaGetLastError());
             }

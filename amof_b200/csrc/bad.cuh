@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad(BadArgs a) {
             if (!(B < 0 || sp[p] == B)) continue;
             for (int q = p + 1; q < nn; ++q) {
                 if (!(B < 0 || sp[q] == B)) continue;
-                const double x = (ux[p] * ux[q] + uy[p] * uy[q]) + uz[p] * uz[q];
-                if (!(fabs(x) <= 1.0)) { atomicAdd(a.dropped + t, 1ull); continue; }   // acos -> NaN, np.histogram drops it
+                double x = (ux[p] * ux[q] + uy[p] * uy[q]) + uz[p] * uz[q];
+                if (x != x) { atomicAdd(a.dropped + t, 1ull); continue; }   // NaN (coincident atoms): np.histogram drops it
+                x = x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x);                   // ase.geometry.get_angles clips 1+2e-16 away before arccos
                 const int k = bad_bin(-x, a.tthr, a.inv_dtheta_f, a.nbins);
                 if (k >= a.nbins) atomicAdd(a.dropped + t, 1ull);
                 else atomicAdd(row + k, 1ull);

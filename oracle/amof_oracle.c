@@ -37,6 +37,8 @@
  *  P5  neighbour criterion (U5): kept iff cutoff[Zi][Zj] > 0 and sqrt(d2) < cutoff[Zi][Zj] (strict).
  *  P6  angle (U6): the two neighbour image vectors v0, v1 of P3 are used (not a second find_mic);
  *      n = sqrt(d2); u = v/n componentwise; x = (u0x*u1x + u0y*u1y) + u0z*u1z;
+ *      x is clipped to [-1, 1] (ase.geometry.get_angles: "we just normalized the vectors, but in some cases
+ *      we can get bad things like 1+2e-16.  These we clip away"; NaN stays NaN, as with np.clip);
  *      theta = acos(x) * (180.0/pi)  [glibc acos of this container].  Precondition: cutoff below
  *      half the smallest perpendicular cell height, else the call is refused.
  *  P7  np.histogram with explicit edges e_k = k*dtheta (k = 0..nbins): bin b iff e_b <= theta < e_{b+1},
@@ -423,12 +425,19 @@ static void bad_cb(void *vctx, int i, int j, const double *dv, double d2) {
     c->nnb[i] = k + 1;
 }
 
+/* degrees(arccos(clip(x, -1, 1))): collinear neighbours land on 0 / 180 degrees, NaN stays NaN (np.clip) */
+double orc_angle_of_cosine(double x) {
+    if (x < -1.0) x = -1.0;
+    if (x > 1.0) x = 1.0;
+    return acos(x) * (180.0 / 3.14159265358979323846);
+}
+
 double orc_angle_deg(const double *v0, double d20, const double *v1, double d21) {
     double n0 = sqrt(d20), n1 = sqrt(d21);
     double u0x = v0[0] / n0, u0y = v0[1] / n0, u0z = v0[2] / n0;
     double u1x = v1[0] / n1, u1y = v1[1] / n1, u1z = v1[2] / n1;
     double x = (u0x * u1x + u0y * u1y) + u0z * u1z;
-    return acos(x) * (180.0 / 3.14159265358979323846);
+    return orc_angle_of_cosine(x);
 }
 
 /* P7: index of the np.histogram bin for edges e_k = k*dtheta, k = 0..nbins; -1 if dropped. */

@@ -48,6 +48,8 @@ def lib():
         L.orc_cell_volume.restype = C.c_double
         L.orc_theta_bin.argtypes = [C.c_double, C.c_double, C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_angle_of_cosine.argtypes = [C.c_double]
+        L.orc_angle_of_cosine.restype = C.c_double
         _lib = L
     return _lib
 
@@ -140,6 +142,11 @@ def bad_hist(pos, cell, spec, nspec, cutoff, A, B, dtheta, nbins, max_cn=32, met
                                float(dtheta), int(nbins), int(max_cn), method, hist.ctypes.data_as(_u64p),
                                C.byref(dropped)), "bad_frame")
     return hist, dropped.value
+
+
+def angle_of_cosine(x):
+    """degrees(arccos(clip(x, -1, 1))) with the container's libm (pin P6)."""
+    return float(lib().orc_angle_of_cosine(float(x)))
 
 
 def bad_angles(pos, cell, spec, nspec, cutoff, A, B, method=1, cap=1 << 20):

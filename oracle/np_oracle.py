@@ -126,7 +126,8 @@ def bad_angles(pos, cell, spec, cutoff, A, B):
             x = (u0[0] * u1[0] + u0[1] * u1[1]) + u0[2] * u1[2]
             # libm acos (math.acos), NOT np.arccos: numpy >= 1.22 ships its own SIMD arccos that differs from
             # glibc in the last ulp; the reference pins numpy 1.21.2, whose float64 arccos is libm's.
-            th = math.acos(float(x)) if -1.0 <= x <= 1.0 else float('nan')
+            x = min(max(float(x), -1.0), 1.0) if x == x else x       # ase clips to [-1, 1] before arccos; NaN stays NaN
+            th = math.acos(x) if x == x else float('nan')
             out.setdefault(cn, []).append(th * (180.0 / math.pi))
     return out
 

@@ -135,3 +135,24 @@ def test_many_frames_streaming(backend, monkeypatch):
     hist, dropped, nf = backend.bad_counts(spec, 2, [(pos[:9], cell[:9]), (pos[9:], cell[9:])], cut, triples, 0.5, 361)
     want, wdrop = _oracle(pos, cell, spec, 2, cut, triples, 0.5, 361)
     assert nf == T and np.array_equal(hist, want) and np.array_equal(dropped, wdrop)
+
+
+def test_cosine_beyond_one_is_clipped(backend):
+    """Exactly collinear neighbours: with v1 = 2 v0 the unit vectors are the same doubles and u.u = 1 + 2^-52, with
+    v1 = -2 v0 it is -(1 + 2^-52).  ase clips the cosine before arccos (0 and 180 degrees); nothing may be dropped."""
+    cell = np.diag([32.0, 32.0, 32.0])
+    c = np.array([16.0, 16.0, 16.0])
+    v = np.array([-4.0, -1.0, -2.0]) / 4.0                      # |v| = 1.1456; every sum below is exact in binary64
+    n = np.sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])
+    u = v / n
+    assert (u[0] * u[0] + u[1] * u[1]) + u[2] * u[2] > 1.0
+    spec = np.array([0, 1, 1], dtype=np.uint8)
+    cut = np.array([[0.0, 2.5], [2.5, 0.0]])
+    for sign, where in ((2.0, 0), (-2.0, -1)):
+        pos = np.vstack([c, c + v, c + sign * v])
+        for dtheta in (0.05, 1.0):
+            nbins = int(180 // dtheta) + 1
+            hist, dropped, _ = backend.bad_counts(spec, 2, [(pos[None], cell[None])], cut, [(0, 1)], dtheta, nbins)
+            want, wdrop = _oracle(pos[None], cell[None], spec, 2, cut, [(0, 1)], dtheta, nbins)
+            assert np.array_equal(hist, want) and int(dropped.sum()) == 0 and int(wdrop.sum()) == 0
+            assert int(hist[0, 2].sum()) == 1 and int(hist[0, 2][where]) == 1      # first bin / the closed last bin

@@ -243,3 +243,29 @@ def test_direct_msd_free_particles():
     got = orc.msd_direct(wrapped, cells, spec, -1)
     want = ((true - true[0]) ** 2).sum(axis=2).mean(axis=1)
     assert np.allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+def test_collinear_neighbours_are_clipped_not_dropped():
+    """ase.geometry.get_angles clips the cosine to [-1, 1] before arccos ("we can get bad things like 1+2e-16"): exactly
+    collinear neighbours whose normalised dot product rounds past +-1 land on 0 / 180 degrees instead of NaN."""
+    cell = np.eye(3) * 30.0
+    c = np.array([15.0, 15.0, 15.0])
+    v0 = np.array([-1.8913201215548283, -0.39184909715672805, -0.2982765861550717])
+    v1 = np.array([-1.5876314148962145, -0.3289300047383363, -0.2503824038621698])
+    u0, u1 = v0 / math.sqrt((v0[0] * v0[0] + v0[1] * v0[1]) + v0[2] * v0[2]), v1 / math.sqrt((v1[0] * v1[0] + v1[1] * v1[1]) + v1[2] * v1[2])
+    assert (u0[0] * u1[0] + u0[1] * u1[1]) + u0[2] * u1[2] > 1.0          # the case the clip exists for
+    spec = np.array([0, 1, 1], dtype=np.uint8)
+    cut = np.array([[0.0, 2.5], [2.5, 0.0]])
+    for sign, want in ((1.0, 0.0), (-1.0, 180.0)):
+        pos = np.vstack([c, c + v0, c + sign * v1])
+        # the frame stores c + v, so the vectors are only nearly collinear; what matters is that nothing is dropped
+        hist, dropped = orc.bad_hist(pos, cell, spec, 2, cut, 0, 1, 0.05, 3600)
+        assert dropped == 0 and int(hist.sum()) == 1
+        assert int(hist[2].argmax()) in ((0, 1) if sign > 0 else (3598, 3599))
+        tw = npo.bad_angles(pos, cell, spec, cut, 0, 1)[2]
+        assert abs(tw[0] - want) < 1e-5
+    # the clipped arithmetic itself: x = 1 + 2^-52 and x = -(1 + 2^-52) give 0 and 180 degrees, never NaN
+    big = np.nextafter(1.0, 2.0)
+    for x, want in ((big, 0.0), (-big, 180.0)):
+        th = orc.angle_of_cosine(x)
+        assert th == want

@@ -9,6 +9,9 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from amof_b200 import _lib, atom as amatom, frames as fr, synth  # noqa: E402
 
+if os.environ.get("AMOFB_LIB"):          # a variant built by tools/build_variants.sh
+    _lib._SO = os.path.abspath(os.environ["AMOFB_LIB"])
+
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 214
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
