@@ -22,6 +22,7 @@ _SO = os.path.join(_HERE, "libamofb.so")
 
 AMOFB_MAX_SPECIES = 16
 AMOFB_BAD_MAX_CN = 32
+AMOFB_OPT_RDF_BIN_RULE = 1
 
 _ERRORS = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: ValueError, -5: MemoryError}
 
@@ -41,6 +42,7 @@ SIGNATURES = {
     "amofb_sync": (C.c_int, [_vp]),
     "amofb_sync_copies": (C.c_int, [_vp]),
     "amofb_launch_count": (C.c_int64, [_vp]),
+    "amofb_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "amofb_set_profiling": (C.c_int, [_vp, C.c_int]),
     "amofb_pair_kernel_time": (C.c_int, [_vp, _dp, _i64p, C.c_int]),
     "amofb_timer_mark": (C.c_int, [_vp, C.c_int]),
@@ -196,6 +198,10 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.amofb_launch_count(self.h))
+
+    def set_option(self, option, value):
+        """amofb_set_option: option names are the AMOFB_OPT_* constants of include/amofb.h"""
+        self.check(self.lib.amofb_set_option(self.h, int(option), int(value)))
 
     def set_profiling(self, on):
         self.check(self.lib.amofb_set_profiling(self.h, 1 if on else 0))

@@ -99,6 +99,19 @@ extern "C" int amofb_sync_copies(amofb_ctx *ctx) {
 
 extern "C" int64_t amofb_launch_count(const amofb_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+extern "C" int amofb_set_option(amofb_ctx *ctx, int option, int value) {
+    if (!ctx) return AMOFB_ERR_ARG;
+    switch (option) {
+        case AMOFB_OPT_RDF_BIN_RULE:
+            if (value != 0 && value != 1) return amofb_fail(ctx, AMOFB_ERR_ARG, "AMOFB_OPT_RDF_BIN_RULE takes 0 (divide) or 1 (multiply)");
+            if (ctx->pair) return amofb_fail(ctx, AMOFB_ERR_STATE, "options cannot change while a pair analysis is open");
+            ctx->rdf_bin_rule = value;
+            return AMOFB_OK;
+        default:
+            return amofb_fail(ctx, AMOFB_ERR_ARG, "unknown option %d", option);
+    }
+}
+
 extern "C" int amofb_set_profiling(amofb_ctx *ctx, int enabled) {
     if (!ctx) return AMOFB_ERR_ARG;
     ctx->profiling = enabled != 0;
@@ -520,16 +533,19 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
     // exact thresholds in d2 (P4, P5)
     std::vector<double> edge2((size_t)nbins + 1, 0.0), cnthr((size_t)p->nkeys, 0.0);
     if (p->has_rdf) {
-        const double dr = rmax / (double)nbins;
-        if (ctx->edge_nbins == nbins && ctx->edge_rmax == rmax && (int)ctx->edge_cache.size() == nbins + 1) {
+        const double dr = rmax / (double)nbins, inv_dr = (double)nbins / rmax;
+        const int rule = ctx->rdf_bin_rule;
+        if (ctx->edge_nbins == nbins && ctx->edge_rmax == rmax && ctx->edge_rule == rule && (int)ctx->edge_cache.size() == nbins + 1) {
             edge2 = ctx->edge_cache;                  // same axis as the previous analysis: reuse the bisected table
         } else {
             for (int b = 1; b <= nbins; ++b) {
                 const double fb = (double)b;
                 double guess = (fb * dr) * (fb * dr);
-                edge2[b] = host_threshold(guess, [&](double t) { return sqrt(t) / dr >= fb; });
+                // pin U1 (what asap3 evaluates is not on disk): the quotient d / dr, or the product d * (nBins / rMax)
+                if (rule == 0) edge2[b] = host_threshold(guess, [&](double t) { return sqrt(t) / dr >= fb; });
+                else edge2[b] = host_threshold(guess, [&](double t) { return sqrt(t) * inv_dr >= fb; });
             }
-            ctx->edge_cache = edge2; ctx->edge_rmax = rmax; ctx->edge_nbins = nbins;
+            ctx->edge_cache = edge2; ctx->edge_rmax = rmax; ctx->edge_nbins = nbins; ctx->edge_rule = rule;
         }
         p->r2max = edge2[nbins];
         p->inv_dr_f = (float)((double)nbins / rmax);

@@ -38,7 +38,8 @@ struct amofb_ctx {
     int device = 0;
     // last RDF threshold table (amof.rdf.CoordinationNumber opens one analysis per frame with the same rmax / bins)
     double edge_rmax = 0.0;
-    int edge_nbins = 0;
+    int edge_nbins = 0, edge_rule = 0;
+    int rdf_bin_rule = 0;         // AMOFB_OPT_RDF_BIN_RULE: 0 bin = (int)(d / (rmax/nbins)), 1 bin = (int)(d * (nbins/rmax))  (pin U1)
     std::vector<double> edge_cache;
     // last bond-angle threshold table (3 600 bisections through libm acos: a few ms, identical for every analysis with
     // the same dtheta / bin count)

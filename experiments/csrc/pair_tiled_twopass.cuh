@@ -11,15 +11,21 @@
 //                 cells too dense even alone are split by rows, or marked "hard" and left to the generic kernel.
 //   k_pair_tiled  persistent blocks over the tile list.
 //
-// Compute phase ("candidates in registers, home atoms broadcast"): the candidates of one home cell -- the runs of all
-// staged rows -- form ONE flat index space; a work item is (home cell, chunk of 32*TILE_K flat candidates).  A warp
-// loads its chunk once (TILE_K candidates per lane, kept in registers) and then walks the home atoms of the cell: the
-// home atom is read with a broadcast shared-memory load (one wavefront), every lane forms its TILE_K distances.  All 32
-// lanes hold candidates whatever the cell populations, and shared-memory traffic is one broadcast per 32*TILE_K
-// distances instead of one 32-byte record per lane and distance (the round-1 kernel: lanes = home atom x sub-lane, one
-// item per (home cell, row); experiments/csrc/pair_tiled_r1.cuh).  A two-pass variant that first drops the candidates
-// farther than the search radius from the bounding sphere of the home atoms (41 % of them) and compacts the rest is in
-// experiments/csrc/pair_tiled_twopass.cuh: bit-exact, but slower.
+// Compute phase, two passes per home cell (the round-1 kernel -- lanes = home atom x sub-lane, one work item per (home
+// cell, row), every candidate of the 5x5x5 half stencil evaluated against every home atom -- is kept for reference in
+// experiments/csrc/pair_tiled_r1.cuh):
+//   pass 1  the candidates of one home cell (the runs of all staged rows) form ONE flat index space; 32 at a time, each
+//           lane tests its candidate against the bounding sphere of the cell's home ATOMS (centroid, largest distance):
+//           a candidate farther than search radius + sphere radius from the centroid cannot pair with any of them.  On
+//           the a-ZIF boxes this drops 41 % of the candidates (the corners of the stencil), i.e. the hit rate of the
+//           distances that are then formed rises from 26 % to 44 %.  Survivors are appended, warp-compacted, to a small
+//           per-warp ring of 16-bit entries.
+//   pass 2  whenever 32*TILE_K survivors wait, every lane loads TILE_K of them into registers and the warp walks the home
+//           atoms of the cell: the home atom is read with a broadcast shared-memory load (one wavefront), every lane forms
+//           its TILE_K distances and bins them branch-free (the increment alone is predicated).  All 32 lanes hold live
+//           candidates whatever the cell populations.
+// A warp owns a contiguous, cost-balanced range of (home cell, 32-candidate batch) pairs of the tile, so the per-cell
+// set-up is paid once or twice per warp and tile.
 //
 // Arithmetic, thresholds, folding of species pairs and histogram privatisation are exactly those of pair.cuh.
 #pragma once
@@ -37,7 +43,8 @@
 #ifndef TILE_HUNROLL
 #define TILE_HUNROLL 1       // home atoms per trip of the inner loop
 #endif
-#define TILE_STATIC_SMEM 2560     // upper bound of the kernel's static shared memory (host-side budget)
+#define TILE_RING 128        // survivor ring per warp (entries); a drain leaves < 32*TILE_K, a batch adds <= 32
+#define TILE_STATIC_SMEM 8192     // upper bound of the kernel's static shared memory (host-side budget)
 #define TILE_CHUNK (32 * TILE_K)
 #define TILE_PRAGMA_(x) _Pragma(#x)
 #define TILE_PRAGMA_UNROLL(n) TILE_PRAGMA_(unroll n)
@@ -238,7 +245,7 @@ __device__ __forceinline__ void reds_inc(unsigned addr) {
 // 32-bit shared addresses of the kernel's tables, derived once per kernel from an opaque base (the asm keeps the
 // compiler from re-materialising S2UR SR_CgaCtaId + ULEA chains next to every use)
 struct SmemAddr {
-    unsigned atoms, edge, cnthr, hist, cn, key, off, pre, code, tvec;
+    unsigned atoms, edge, cnthr, hist, cn, key, off, pre, code, tvec, sph;
 };
 __device__ __forceinline__ unsigned opaque_u32(unsigned v) {
     unsigned r;
@@ -261,34 +268,28 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
     return v;
 }
 
-// The K candidates of every lane (in registers) against the nh home atoms of one cell, read by broadcast loads.
+// ---- pass 2: K survivors per lane (in registers) against the nh home atoms of one cell -------------------------
+// The home atom is read by broadcast loads (same address in every lane: one wavefront).  With a hit rate near 45 % some
+// lane always hits, so the binning is branch-free and the histogram increment of a lane that does not count goes to a
+// scratch word instead of sitting behind a divergent branch.
 //   SHIFT: some candidate of the chunk sits in a periodic image; without it (pj - pi) + 0 == pj - pi bit for bit (up to
 //          the sign of a zero, which the squares drop), so the adds go.
-//   AFTER: the chunk holds candidates of the home cell itself: the pair (home h, own-cell candidate f) counts iff f > h,
-//          passed as hlim[k] = f (nh for every other candidate).
-//   CN_WIDE: some cutoff exceeds rmax, so a candidate inside r2search can still be outside the RDF range.
-template <bool HAS_CN, bool CN_WIDE, bool SHIFT, bool AFTER, int K>
-__device__ __forceinline__ void bcast_scan(const PairArgs &a, const SmemAddr &sa, unsigned haddr, int nh,
+//   hlim:  a candidate f of the home cell itself pairs with home atom h iff f > h (the other orientation is the same
+//          unordered pair); every other candidate carries hlim = nh, an empty slot hlim = 0.
+//   CN_WIDE: some cutoff exceeds rmax, so a candidate inside the search radius can still be outside the RDF range.
+template <bool HAS_CN, bool CN_WIDE, bool SHIFT, int K>
+__device__ __forceinline__ void bcast_scan(const PairArgs &a, const SmemAddr &sa, unsigned trash_addr, unsigned haddr, int nh,
                                            const double (&cx)[K], const double (&cy)[K], const double (&cz)[K],
                                            const unsigned (&krow)[K], const double (&Tx)[K], const double (&Ty)[K],
                                            const double (&Tz)[K], const int (&hlim)[K]) {
-    const double r2search = a.r2search, r2max = a.r2max, cn_r2max = a.cn_r2max;
+    const double r2max = a.r2max, cn_r2max = a.cn_r2max;
     const float inv_dr_f = a.inv_dr_f, margin = a.bin_margin;
     const int nbins = a.nbins;
-    const unsigned edge_addr = sa.edge, hist_addr = sa.hist, cnthr_addr = sa.cnthr, cn_addr = sa.cn;
-    // the hit work: exact bin + shared-memory increment (the host only selects this kernel when margin > 0)
-    auto hit = [&](double dd, unsigned kaddr) {
-        const int key = lds_u16(kaddr);
-        if (!CN_WIDE || dd < r2max) {             // r2search == r2max unless a cutoff reaches beyond rmax
-            const int b = rdf_bin_s(dd, edge_addr, inv_dr_f, margin);
-            reds_inc(hist_addr + 4u * (unsigned)(key * nbins + b));
-        }
-        if (HAS_CN && dd < cn_r2max && dd < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
-    };
+    const unsigned edge_addr = sa.edge + 8u, hist_addr = sa.hist, cnthr_addr = sa.cnthr, cn_addr = sa.cn;
     TILE_PRAGMA_UNROLL(TILE_HUNROLL)
     for (int h = 0; h < nh; ++h, haddr += 32u) {
         double hx, hy, hz;
-        lds_xyz(haddr, hx, hy, hz);                                   // same address in every lane: one wavefront
+        lds_xyz(haddr, hx, hy, hz);
         const unsigned si2 = 2u * (unsigned)lds_species(haddr);
         double dd[K];
 #pragma unroll
@@ -298,65 +299,66 @@ __device__ __forceinline__ void bcast_scan(const PairArgs &a, const SmemAddr &sa
             dd[k] = (dx * dx + dy * dy) + dz * dz;
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-            if (dd[k] < r2search && (!AFTER || h < hlim[k])) hit(dd[k], krow[k] + si2);
+        for (int k = 0; k < K; ++k) {
+            const bool mine = h < hlim[k];
+            const int key = lds_u16(krow[k] + si2);
+            // exact P4 bin: fp32 estimate biased down by the proven margin, settled by ONE comparison (see rdf_bin)
+            int b = (int)fmaf(sqrt_approx((float)dd[k]), inv_dr_f, -margin);
+            b = min(b, nbins - 1);                                       // lanes beyond rmax: keep the table read in bounds
+            const int idx = key * nbins + b + (dd[k] >= lds_f64(edge_addr + 8u * (unsigned)b) ? 1 : 0);
+            reds_inc((mine & (dd[k] < r2max)) ? hist_addr + 4u * (unsigned)idx : trash_addr);
+            if (HAS_CN) {
+                if (mine & (dd[k] < cn_r2max)) {                         // a few per cent of the pairs
+                    if (dd[k] < lds_f64(cnthr_addr + 8u * (unsigned)key)) reds_inc(cn_addr + 4u * (unsigned)key);
+                }
+            }
+        }
     }
 }
 
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory");
+}
 __device__ __forceinline__ int lds_u8(unsigned addr) {
     unsigned v;
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return (int)v;
 }
 
-// One chunk: the flat candidates [base, base + 32*K) of the home cell described by pre_a, against its nh home atoms.
-// rr0: the row that holds flat index `base`.
+// load the survivors [head, head + n) of the warp's ring (n <= 32*K) into registers and run the home atoms over them
 template <bool HAS_CN, bool CN_WIDE, int K>
-__device__ __forceinline__ void chunk(const PairArgs &a, const SmemAddr &sa, unsigned pre_a, int rr0, int base, int F, int lane,
-                                      unsigned haddr, int nh, bool after, bool tile_img) {
+__device__ __forceinline__ void pass2(const PairArgs &a, const SmemAddr &sa, unsigned ring_addr, unsigned trash_addr, unsigned head, int n,
+                                      int lane, unsigned haddr, int nh, int own_off, bool tile_img) {
     double cx[K], cy[K], cz[K], Tx[K], Ty[K], Tz[K];
     unsigned krow[K];
     int hlim[K];
     bool shifted = false;
-    // walk state: staged index = flat index + joff while flat index < nstart
-    int rr = rr0 - 1, next = lds_s32(pre_a + 4u * (unsigned)rr0), joff = 0, nstart = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int fl = base + k * 32 + lane;
+        const int i = k * 32 + lane;
+        // an empty slot re-reads the chunk's first survivor and never counts (hlim = 0)
+        const unsigned e = (unsigned)lds_u16(ring_addr + 2u * ((head + (unsigned)(i < n ? i : 0)) & (TILE_RING - 1)));
+        const int j = (int)(e & 0x7ffu);
+        const unsigned addr = sa.atoms + (unsigned)j * 32u;
+        lds_xyz(addr, cx[k], cy[k], cz[k]);
+        krow[k] = sa.key + 2u * (unsigned)(lds_species(addr) * a.n_species);
+        const unsigned o = (unsigned)(j - own_off);                      // position inside the home cell when it is its row-0 copy
+        hlim[k] = i < n ? (o < (unsigned)nh ? (int)o : nh) : 0;
         Tx[k] = Ty[k] = Tz[k] = 0.0;
-        hlim[k] = nh;
-        if (fl < F) {
-            while (fl >= nstart) {
-                ++rr;
-                joff = (next >> 16) - (next & 0xffff);
-                next = lds_s32(pre_a + 4u * (unsigned)(rr + 1));
-                nstart = next & 0xffff;
+        if (tile_img) {
+            const unsigned code = e >> 11;
+            if (code != 13u) {
+                const unsigned ta = sa.tvec + 24u * code;
+                Tx[k] = lds_f64(ta); Ty[k] = lds_f64(ta + 8u); Tz[k] = lds_f64(ta + 16u);
+                shifted = true;
             }
-            const int j = fl + joff;
-            const unsigned addr = sa.atoms + (unsigned)j * 32u;
-            lds_xyz(addr, cx[k], cy[k], cz[k]);
-            krow[k] = sa.key + 2u * (unsigned)(lds_species(addr) * a.n_species);
-            if (after && fl < nh) hlim[k] = fl;                          // a candidate of the home cell itself
-            if (tile_img) {
-                const unsigned code = (unsigned)lds_u8(sa.code + (unsigned)j);
-                if (code != 13u) {
-                    const unsigned ta = sa.tvec + 24u * code;
-                    Tx[k] = lds_f64(ta); Ty[k] = lds_f64(ta + 8u); Tz[k] = lds_f64(ta + 16u);
-                    shifted = true;
-                }
-            }
-        } else {
-            cx[k] = cy[k] = cz[k] = 1e300;                               // d2 = inf: below no threshold
-            krow[k] = sa.key;
         }
     }
-    if (tile_img && __any_sync(0xffffffffu, shifted)) {
-        if (after) bcast_scan<HAS_CN, CN_WIDE, true, true, K>(a, sa, haddr, nh, cx, cy, cz, krow, Tx, Ty, Tz, hlim);
-        else bcast_scan<HAS_CN, CN_WIDE, true, false, K>(a, sa, haddr, nh, cx, cy, cz, krow, Tx, Ty, Tz, hlim);
-    } else {
-        if (after) bcast_scan<HAS_CN, CN_WIDE, false, true, K>(a, sa, haddr, nh, cx, cy, cz, krow, Tx, Ty, Tz, hlim);
-        else bcast_scan<HAS_CN, CN_WIDE, false, false, K>(a, sa, haddr, nh, cx, cy, cz, krow, Tx, Ty, Tz, hlim);
-    }
+    __syncwarp();                                                        // ring slots are free for the next appends
+    if (tile_img && __any_sync(0xffffffffu, shifted))
+        bcast_scan<HAS_CN, CN_WIDE, true, K>(a, sa, trash_addr, haddr, nh, cx, cy, cz, krow, Tx, Ty, Tz, hlim);
+    else
+        bcast_scan<HAS_CN, CN_WIDE, false, K>(a, sa, trash_addr, haddr, nh, cx, cy, cz, krow, Tx, Ty, Tz, hlim);
 }
 
 template <bool HAS_CN, bool CN_WIDE>
@@ -380,6 +382,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_rowimg[TILE_MAX_ROWS];        // per staged row: image (s0 | s1 << 16) of its column
     __shared__ double s_tvec[27 * 3];              // image shift T(s0, s1, s2), s in {-1, 0, 1}^3, code = (s0+1) + 3 (s1+1) + 9 (s2+1)
+    __shared__ double s_sph[TILE_MAX_ZLEN * 4];    // per home cell: centroid of its atoms, (search radius + largest distance from it)^2
+    __shared__ unsigned short s_ring[(TILE_THREADS / 32) * TILE_RING];
+    __shared__ unsigned s_trash;
     SmemAddr sa;
     {
         const unsigned sb = opaque_u32((unsigned)__cvta_generic_to_shared(smem_raw));
@@ -393,10 +398,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
         sa.pre = sb + (unsigned)(reinterpret_cast<unsigned char *>(s_pre) - smem_raw);
         sa.code = sb + (unsigned)(s_code - smem_raw);
         sa.tvec = opaque_u32((unsigned)__cvta_generic_to_shared(s_tvec));
+        sa.sph = opaque_u32((unsigned)__cvta_generic_to_shared(s_sph));
     }
 
     const int S = a.n_species;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = TILE_THREADS / 32;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned ring_addr = opaque_u32((unsigned)__cvta_generic_to_shared(s_ring)) + 2u * (unsigned)(warp * TILE_RING);
+    const unsigned trash_addr = opaque_u32((unsigned)__cvta_generic_to_shared(&s_trash));
     for (int k = threadIdx.x; k <= a.nbins; k += blockDim.x) s_edge2[k] = a.edge2[k];
     for (int k = threadIdx.x; k < a.nkeys * a.nbins; k += blockDim.x) s_hist[k] = 0u;
     if (HAS_CN)
@@ -404,8 +413,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
     for (int k = threadIdx.x; k < S * S; k += blockDim.x) s_key[k] = a.keyidx[k];
 
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    if (threadIdx.x == 0) { mbar_init(mbar, 1); s_trash = 0u; }
     unsigned tma_phase = 0;
+    const double rsearch = sqrt(a.r2search);
     const int n_tiles = min(*ta.n_tiles, ta.max_tiles);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();     // previous tile fully consumed (atoms, offsets, geometry, cn counters)
@@ -535,30 +545,114 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) k_pair_tiled(Ti
         if (threadIdx.x == 0) mbar_wait(mbar, tma_phase);     // one poller; 511 spinning threads would eat issue slots
         tma_phase ^= 1u;
         __syncthreads();
+        // bounding sphere of the home atoms of every home cell (thread = home cell; the cells hold ~8 atoms)
+        if (threadIdx.x < zlen) {
+            const int hb = s_off[E + threadIdx.x], he = s_off[E + threadIdx.x + 1];
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            for (int i = hb; i < he; ++i) {
+                double x, y, z;
+                lds_xyz(sa.atoms + (unsigned)i * 32u, x, y, z);
+                sx += x; sy += y; sz += z;
+            }
+            const double inv_n = he > hb ? 1.0 / (double)(he - hb) : 0.0;
+            sx *= inv_n; sy *= inv_n; sz *= inv_n;
+            double r2 = 0.0;
+            for (int i = hb; i < he; ++i) {
+                double x, y, z;
+                lds_xyz(sa.atoms + (unsigned)i * 32u, x, y, z);
+                x -= sx; y -= sy; z -= sz;
+                r2 = fmax(r2, (x * x + y * y) + z * z);
+            }
+            const double reach = (rsearch + sqrt(r2)) * (1.0 + 1e-9);   // the test below is formed in another operation order than P3
+            double *sp = s_sph + 4 * threadIdx.x;
+            sp[0] = sx; sp[1] = sy; sp[2] = sz; sp[3] = reach * reach;
+        }
+        __syncthreads();
 
         // ---- compute --------------------------------------------------------------------------------------
-        // items = (home cell, chunk of its flat candidate space) in home-cell order; lane = home cell: every warp keeps the
-        // inclusive prefix of the chunk counts in a register and finds the cell of an item with one ballot
-        int nc_l = 0;
-        if (lane < zlen && s_off[E + lane + 1] > s_off[E + lane]) nc_l = (s_pre[lane * (RR + 1) + RR] + TILE_CHUNK - 1) / TILE_CHUNK;
-        const int ci_l = warp_incl_scan_i(nc_l, lane);
-        const int n_items = __shfl_sync(0xffffffffu, ci_l, 31);
-        for (int item = warp; item < n_items; item += nwarp) {
-            const int hz = __popc(__ballot_sync(0xffffffffu, ci_l <= item));      // cells wholly before this item
-            const int base = (item - __shfl_sync(0xffffffffu, ci_l - nc_l, hz)) * TILE_CHUNK;
+        // lane = home cell: 32-candidate batches nb, cost weight w per batch (pass 1 + its share of pass 2, in units of
+        // one home atom), inclusive prefix of nb * w.  Warp `warp` owns the weight interval [W warp / nwarp, W (warp+1) / nwarp).
+        int hz, b, hz_e, b_e;
+        {
+            int F_l = 0, nh_l = 0;
+            if (lane < zlen) { F_l = s_pre[lane * (RR + 1) + RR]; nh_l = s_off[E + lane + 1] - s_off[E + lane]; }
+            const int nb_l = nh_l > 0 ? (F_l + 31) >> 5 : 0;
+            const int w_l = nh_l + 3;
+            const int cw_l = warp_incl_scan_i(nb_l * w_l, lane);
+            const int W = __shfl_sync(0xffffffffu, cw_l, 31);
+            const int x0 = (int)(((long long)W * warp) / nwarp), x1 = (int)(((long long)W * (warp + 1)) / nwarp);
+            hz = __popc(__ballot_sync(0xffffffffu, cw_l <= x0));
+            hz_e = __popc(__ballot_sync(0xffffffffu, cw_l <= x1));
+            const int e0 = __shfl_sync(0xffffffffu, cw_l - nb_l * w_l, hz & 31), w0 = __shfl_sync(0xffffffffu, w_l, hz & 31);
+            const int e1 = __shfl_sync(0xffffffffu, cw_l - nb_l * w_l, hz_e & 31), w1 = __shfl_sync(0xffffffffu, w_l, hz_e & 31);
+            b = hz < 32 ? (x0 - e0) / w0 : 0;
+            b_e = hz_e < 32 ? (x1 - e1) / w1 : 0;
+        }
+        while (hz < zlen && (hz < hz_e || (hz == hz_e && b < b_e))) {
+            // ---- the batches [b, b_end) of home cell hz ----
             const int hb = s_off[E + hz], nh = s_off[E + hz + 1] - hb;
             const unsigned pre_a = sa.pre + 4u * (unsigned)(hz * (RR + 1));
             const int F = lds_s32(pre_a + 4u * (unsigned)RR);
-            // first row of the chunk: the last row whose flat start is <= base (row starts are non-decreasing)
-            int rr0 = -1;
-            for (int r0 = 0; r0 < RR; r0 += 32) {
-                const int p = r0 + lane < RR ? (lds_s32(pre_a + 4u * (unsigned)(r0 + lane)) & 0xffff) : 0x7fffffff;
-                rr0 += __popc(__ballot_sync(0xffffffffu, p <= base));
+            const int nb = nh > 0 ? (F + 31) >> 5 : 0;
+            const int b_end = hz == hz_e ? b_e : nb;
+            if (b < b_end) {
+                const unsigned haddr = sa.atoms + (unsigned)hb * 32u;
+                const int own_off = rb == 0 ? (lds_s32(pre_a) >> 16) : -0x10000;       // the home cell's copy inside row 0
+                const unsigned sph_a = sa.sph + 32u * (unsigned)hz;
+                int base = b * 32;
+                // first row of the first batch: the last row whose flat start is <= base (row starts are non-decreasing)
+                int rr = -1;
+                for (int r0 = 0; r0 < RR; r0 += 32) {
+                    const int p = r0 + lane < RR ? (lds_s32(pre_a + 4u * (unsigned)(r0 + lane)) & 0xffff) : 0x7fffffff;
+                    rr += __popc(__ballot_sync(0xffffffffu, p <= base));
+                }
+                int next = lds_s32(pre_a + 4u * (unsigned)rr);
+                int joff = 0, nstart = 0;           // staged index = flat index + joff while flat index < nstart
+                --rr;                               // the walk below opens row rr + 1 first
+                unsigned head = 0, tail = 0;
+                for (; b < b_end; ++b, base += 32) {
+                    // -- pass 1: 32 flat candidates against the bounding sphere of the home atoms
+                    const int fl = base + lane;
+                    bool keep = false;
+                    unsigned entry = 0;
+                    if (fl < F) {
+                        while (fl >= nstart) {
+                            ++rr;
+                            joff = (next >> 16) - (next & 0xffff);
+                            next = lds_s32(pre_a + 4u * (unsigned)(rr + 1));
+                            nstart = next & 0xffff;
+                        }
+                        const int j = fl + joff;
+                        double px, py, pz;
+                        lds_xyz(sa.atoms + (unsigned)j * 32u, px, py, pz);
+                        entry = (unsigned)j | (13u << 11);
+                        if (tile_img) {
+                            const unsigned code = (unsigned)lds_u8(sa.code + (unsigned)j);
+                            entry = (unsigned)j | (code << 11);
+                            if (code != 13u) {
+                                const unsigned ta_ = sa.tvec + 24u * code;
+                                px += lds_f64(ta_); py += lds_f64(ta_ + 8u); pz += lds_f64(ta_ + 16u);
+                            }
+                        }
+                        const double ex = px - lds_f64(sph_a), ey = py - lds_f64(sph_a + 8u), ez = pz - lds_f64(sph_a + 16u);
+                        keep = __fma_rn(ez, ez, __fma_rn(ey, ey, ex * ex)) < lds_f64(sph_a + 24u);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) sts_u16(ring_addr + 2u * ((tail + (unsigned)__popc(m & lt_mask)) & (TILE_RING - 1)), entry);
+                    tail += (unsigned)__popc(m);
+                    __syncwarp();
+                    // -- pass 2 whenever a full chunk waits
+                    if (tail - head >= (unsigned)TILE_CHUNK) {
+                        pass2<HAS_CN, CN_WIDE, TILE_K>(a, sa, ring_addr, trash_addr, head, TILE_CHUNK, lane, haddr, nh, own_off, tile_img);
+                        head += TILE_CHUNK;
+                    }
+                }
+                // the rest of this cell's survivors: the narrowest loop that holds them
+                const int rem = (int)(tail - head);
+                if (TILE_K > 1 && rem > 32) pass2<HAS_CN, CN_WIDE, TILE_K>(a, sa, ring_addr, trash_addr, head, rem, lane, haddr, nh, own_off, tile_img);
+                else if (rem > 0) pass2<HAS_CN, CN_WIDE, 1>(a, sa, ring_addr, trash_addr, head, rem, lane, haddr, nh, own_off, tile_img);
             }
-            const unsigned haddr = sa.atoms + (unsigned)hb * 32u;
-            const bool after = rb == 0 && base < nh;          // row 0 opens with the home cell itself
-            if (TILE_K > 1 && F - base <= 32) chunk<HAS_CN, CN_WIDE, 1>(a, sa, pre_a, rr0, base, F, lane, haddr, nh, after, tile_img);
-            else chunk<HAS_CN, CN_WIDE, TILE_K>(a, sa, pre_a, rr0, base, F, lane, haddr, nh, after, tile_img);
+            ++hz; b = 0;
         }
         if (HAS_CN) {
             __syncthreads();

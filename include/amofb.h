@@ -56,6 +56,13 @@ int amofb_sync(amofb_ctx *ctx);
 int amofb_sync_copies(amofb_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py reports it as gpu_launches). */
 int64_t amofb_launch_count(const amofb_ctx *ctx);
+/* Conventions of the upstream packages that cannot be read off their sources here (asap3 / ase are not on disk,
+ * SURVEY.md 8(c) U1-U6) are options with the oracle's pin as default:
+ *   AMOFB_OPT_RDF_BIN_RULE  0: bin = (int)(d / (rMax/nBins))   (default, pin U1)
+ *                           1: bin = (int)(d * (nBins/rMax))
+ * Set between analyses (AMOFB_ERR_STATE while a pair analysis is open). */
+#define AMOFB_OPT_RDF_BIN_RULE 1
+int amofb_set_option(amofb_ctx *ctx, int option, int value);
 /* Sum of CUDA-event durations (ms) and launch count of the pair kernel since the last call with
  * reset != 0; timing is only collected after amofb_set_profiling(ctx, 1). */
 int amofb_set_profiling(amofb_ctx *ctx, int enabled);

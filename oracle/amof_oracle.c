@@ -58,6 +58,15 @@
 #include <omp.h>
 #endif
 
+/* ---- named conventions: what asap3 / ase really evaluate cannot be read here, so the
+ * choices that decide a last-ulp bin are switches with the pin as default.  Process-wide; tests set and restore them.
+ *   bin_rule 0 (pin U1): bin = (int)(d / (rMax/nBins))        1: bin = (int)(d * (nBins/rMax))
+ *   dv_rule  0 (pin P2/P3): atoms are wrapped into the cell first, dv = (pw_j - pw_i) + T(S)
+ *            1: ase.neighborlist's form on the positions as given, dv = (p_j - p_i) + T(S + w_i - w_j), w = floor(f)
+ *               (identical bits whenever every atom already lies inside the cell; brute-force enumeration only) */
+static int g_bin_rule = 0, g_dv_rule = 0;
+void orc_set_conventions(int bin_rule, int dv_rule) { g_bin_rule = bin_rule; g_dv_rule = dv_rule; }
+
 #define ORC_OK 0
 #define ORC_ERR_ARG -1
 #define ORC_ERR_GEOM -4
@@ -141,7 +150,8 @@ static inline void image_shift(const double *cell, int s0, int s1, int s2, doubl
  */
 typedef void (*pair_cb)(void *ctx, int i, int j, const double *dv, double d2);
 
-static int visit_pairs_brute(int n, const double *pw, const double *cell, double rcut, pair_cb cb, void *ctx) {
+static int visit_pairs_brute(int n, const double *pw, const double *cell, double rcut, pair_cb cb, void *ctx,
+                             const double *raw) {
     double inv[9], h[3];
     int rc = orc_cell_inverse(cell, inv);
     if (rc) return rc;
@@ -160,7 +170,16 @@ static int visit_pairs_brute(int n, const double *pw, const double *cell, double
                         if (self_image && i == j) continue;
                         double dv[3];
                         double d2 = pair_d2(pw + 3 * i, pw + 3 * j, T, dv);
-                        if (d2 <= r2pad) cb(ctx, i, j, dv, d2);
+                        if (raw && d2 <= r2pad) {
+                            /* dv_rule 1: same (i, j, image), evaluated on the positions as given */
+                            double fi[3], fj[3], Tr[3];
+                            frac_of(raw + 3 * i, inv, fi);
+                            frac_of(raw + 3 * j, inv, fj);
+                            image_shift(cell, s0 + (int)floor(fi[0]) - (int)floor(fj[0]), s1 + (int)floor(fi[1]) - (int)floor(fj[1]),
+                                        s2 + (int)floor(fi[2]) - (int)floor(fj[2]), Tr);
+                            d2 = pair_d2(raw + 3 * i, raw + 3 * j, Tr, dv);
+                            cb(ctx, i, j, dv, d2);         /* callbacks re-test d2 against their own thresholds */
+                        } else if (d2 <= r2pad) cb(ctx, i, j, dv, d2);
                     }
             }
     return ORC_OK;
@@ -240,7 +259,8 @@ static int visit_pairs(int method, int n, const double *pos, const double *cell,
     double *fr = (double *)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
     if (!pw || !fr) { free(pw); free(fr); return ORC_ERR_MEM; }
     int rc = orc_wrap_positions(n, pos, cell, pw, fr);
-    if (!rc) rc = method == 0 ? visit_pairs_brute(n, pw, cell, rcut, cb, ctx)
+    if (!rc && g_dv_rule != 0 && method != 0) rc = ORC_ERR_ARG;          /* dv_rule 1 exists for the brute-force form only */
+    if (!rc) rc = method == 0 ? visit_pairs_brute(n, pw, cell, rcut, cb, ctx, g_dv_rule ? pos : NULL)
                               : visit_pairs_cells(n, pw, fr, cell, rcut, cb, ctx);
     free(pw); free(fr);
     return rc;
@@ -248,14 +268,14 @@ static int visit_pairs(int method, int n, const double *pos, const double *cell,
 
 /* ------------------------------------------------------------------ RDF (P4) */
 typedef struct {
-    const uint8_t *spec; int nspec; int nbins; double dr; uint64_t *hist;
+    const uint8_t *spec; int nspec; int nbins; double dr, inv_dr; uint64_t *hist;
 } rdf_ctx;
 
 static void rdf_cb(void *vctx, int i, int j, const double *dv, double d2) {
     (void)dv;
     rdf_ctx *c = (rdf_ctx *)vctx;
     double d = sqrt(d2);
-    double q = d / c->dr;
+    double q = g_bin_rule == 0 ? d / c->dr : d * c->inv_dr;
     if (q < (double)c->nbins) {
         int b = (int)q;
         c->hist[((size_t)c->spec[i] * c->nspec + c->spec[j]) * c->nbins + b] += 1;
@@ -266,7 +286,7 @@ static void rdf_cb(void *vctx, int i, int j, const double *dv, double d2) {
 int orc_rdf_frame(int n, const double *pos, const double *cell, const uint8_t *spec, int nspec,
                   double rmax, int nbins, int method, uint64_t *hist) {
     if (n < 0 || nspec < 1 || nbins < 1 || !(rmax > 0.0)) return ORC_ERR_ARG;
-    rdf_ctx c = {spec, nspec, nbins, rmax / nbins, hist};
+    rdf_ctx c = {spec, nspec, nbins, rmax / nbins, (double)nbins / rmax, hist};
     return visit_pairs(method, n, pos, cell, rmax, rdf_cb, &c);
 }
 

@@ -49,6 +49,8 @@ def lib():
         L.orc_theta_bin.argtypes = [C.c_double, C.c_double, C.c_int]
         L.orc_max_threads.restype = C.c_int
         L.orc_angle_of_cosine.argtypes = [C.c_double]
+        L.orc_set_conventions.argtypes = [C.c_int, C.c_int]
+        L.orc_set_conventions.restype = None
         L.orc_angle_of_cosine.restype = C.c_double
         _lib = L
     return _lib
@@ -142,6 +144,11 @@ def bad_hist(pos, cell, spec, nspec, cutoff, A, B, dtheta, nbins, max_cn=32, met
                                float(dtheta), int(nbins), int(max_cn), method, hist.ctypes.data_as(_u64p),
                                C.byref(dropped)), "bad_frame")
     return hist, dropped.value
+
+
+def set_conventions(bin_rule=0, dv_rule=0):
+    """Process-wide switches of the C oracle (see the header of amof_oracle.c); call again with no arguments to restore the pins."""
+    lib().orc_set_conventions(int(bin_rule), int(dv_rule))
 
 
 def angle_of_cosine(x):

@@ -11,6 +11,11 @@ from amof_b200 import _lib, atom as amatom, frames as fr, synth  # noqa: E402
 
 if os.environ.get("AMOFB_LIB"):          # a variant built by tools/build_variants.sh
     _lib._SO = os.path.abspath(os.environ["AMOFB_LIB"])
+    import ctypes
+    _old = ctypes.CDLL(_lib._SO)            # older variants may lack newer entry points: time what they have
+    for _name in list(_lib.SIGNATURES):
+        if not hasattr(_old, _name):
+            _lib.SIGNATURES.pop(_name)
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 214
