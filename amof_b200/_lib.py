@@ -76,6 +76,13 @@ SIGNATURES = {
     "amofb_msd_unwrap": (C.c_int, [_vp]),
     "amofb_msd_com_sums": (C.c_int, [_vp, _dp]),
     "amofb_msd_set_com": (C.c_int, [_vp, _dp]),
+    "amofb_msd_slab_frames": (C.c_int, [_vp, _ip]),
+    "amofb_msd_slab_sums": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _dp]),
+    "amofb_msd_slab_sums_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _dp]),
+    "amofb_msd_slab_sums_begin": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "amofb_msd_slab_sums_begin_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "amofb_msd_slab_sums_wait": (C.c_int, [_vp, _dp]),
+    "amofb_msd_slab_commit": (C.c_int, [_vp, _dp]),
     "amofb_msd_window": (C.c_int, [_vp, C.c_int, _ip, _dp]),
     "amofb_msd_direct": (C.c_int, [_vp, _dp]),
     "amofb_msd_get_positions": (C.c_int, [_vp, _dp]),
@@ -164,9 +171,8 @@ class Context:
         need = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ent = self._scratch.get(name)
         if ent is None or ent[1] < need:
-            if ent is not None:
-                self.lib.amofb_host_free(self.h, ent[0])
-                self._pinned = [q for q in self._pinned if q.value != ent[0].value]
+            # a grown buffer gets a NEW block; the old one stays allocated until close(): a suspended generator of
+            # frames.iter_chunks (or any caller) may still hold a numpy view of it
             p = _vp()
             self.check(self.lib.amofb_host_alloc(self.h, max(need, 1), C.byref(p)))
             self._pinned.append(p)
@@ -174,6 +180,16 @@ class Context:
             self._scratch[name] = ent
         buf = (C.c_char * ent[1]).from_address(ent[0].value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pinned_free(self, arr):
+        """Give back a block obtained from :meth:`pinned_empty` (the array must not be used afterwards)."""
+        addr = arr.ctypes.data
+        for q in self._pinned:
+            if q.value == addr:
+                self._pinned.remove(q)
+                self.check(self.lib.amofb_host_free(self.h, q))
+                return
+        raise ValueError("not a pinned_empty block of this context")
 
     def device_alloc(self, nbytes):
         p = _vp()
@@ -339,7 +355,8 @@ class GpuBackend:
 
 
 class _MsdSession:
-    """amofb_msd_* state machine: load -> [unwrap] -> com_sums -> set_com -> window | direct -> close."""
+    """amofb_msd_* state machine: load -> [unwrap] -> com_sums -> set_com -> window | direct -> close,
+    or the streaming path: (slab_sums -> slab_commit) per slab of frames, in order -> window -> close."""
 
     def __init__(self, backend, T, n, S):
         self.b, self.T, self.n, self.S = backend, T, n, S
@@ -355,6 +372,52 @@ class _MsdSession:
             raise ValueError("positions chunk has shape %r, expected (F, %d, 3)" % (pos.shape, self.n))
         ctx.check(ctx.lib.amofb_msd_load(ctx.h, int(first), pos.shape[0], pos.ctypes.data))
         ctx.sync_copies()
+
+    def slab_frames(self):
+        """frames a host slab may hold (amofb_msd_slab_frames)"""
+        ctx = self.b.ctx
+        n = C.c_int(0)
+        ctx.check(ctx.lib.amofb_msd_slab_frames(ctx.h, C.byref(n)))
+        return int(n.value)
+
+    def slab_sums(self, first, pos):
+        """-> float64[count][4] = (sum m x, sum m y, sum m z, sum m) of the local atoms of every frame of the slab"""
+        ctx = self.b.ctx
+        if isinstance(pos, tuple):        # (device pointer, count)
+            count = int(pos[1])
+            out = np.zeros((count, 4), dtype=np.float64)
+            ctx.check(ctx.lib.amofb_msd_slab_sums_device(ctx.h, int(first), count, pos[0], _ptr(out, _dp)))
+            return out
+        pos = _f64(pos)
+        if pos.ndim != 3 or pos.shape[1:] != (self.n, 3):
+            raise ValueError("positions slab has shape %r, expected (F, %d, 3)" % (pos.shape, self.n))
+        out = np.zeros((pos.shape[0], 4), dtype=np.float64)
+        ctx.check(ctx.lib.amofb_msd_slab_sums(ctx.h, int(first), pos.shape[0], pos.ctypes.data, _ptr(out, _dp)))
+        return out
+
+    def slab_sums_begin(self, first, pos):
+        """enqueue the sums of a slab (at most two slabs may await their commit); returns the number of frames"""
+        ctx = self.b.ctx
+        if isinstance(pos, tuple):        # (device pointer, count)
+            ctx.check(ctx.lib.amofb_msd_slab_sums_begin_device(ctx.h, int(first), int(pos[1]), pos[0]))
+            return int(pos[1])
+        pos = _f64(pos)
+        if pos.ndim != 3 or pos.shape[1:] != (self.n, 3):
+            raise ValueError("positions slab has shape %r, expected (F, %d, 3)" % (pos.shape, self.n))
+        ctx.check(ctx.lib.amofb_msd_slab_sums_begin(ctx.h, int(first), pos.shape[0], pos.ctypes.data))
+        self._keep = pos                  # the copy may still be in flight
+        return pos.shape[0]
+
+    def slab_sums_wait(self, count):
+        ctx = self.b.ctx
+        out = np.zeros((int(count), 4), dtype=np.float64)
+        ctx.check(ctx.lib.amofb_msd_slab_sums_wait(ctx.h, _ptr(out, _dp)))
+        return out
+
+    def slab_commit(self, com):
+        ctx = self.b.ctx
+        com = _f64(com).reshape(-1, 3)
+        ctx.check(ctx.lib.amofb_msd_slab_commit(ctx.h, _ptr(com, _dp)))
 
     def unwrap(self):
         ctx = self.b.ctx

@@ -19,6 +19,17 @@
 
 #include "../../include/amofb.h"
 
+// NVTX ranges around the host-side phases (header-only NVTX3: no library to link; a no-op unless a tool is attached)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+struct nvtx_range {
+    explicit nvtx_range(const char *name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
+#else
+struct nvtx_range { explicit nvtx_range(const char *) {} };
+#endif
+
 #define AMOFB_VERSION_STRING "amofb 0.1 (sm_100a)"
 
 struct PairState;
@@ -215,4 +226,28 @@ __device__ __forceinline__ void wrap_cell(int t, int n, int &s, int &q) {
 
 __device__ __forceinline__ unsigned long long atomicAdd64(unsigned long long *p, unsigned long long v) {
     return atomicAdd(p, v);
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier ----------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" :: "r"(mbar), "r"(parity) : "memory");
 }

@@ -562,3 +562,299 @@ __global__ void __launch_bounds__(128) k_msd_direct(double *__restrict__ P, cons
         p[3 * (size_t)t] = s2;
     }
 }
+
+// =====================================================================================================================
+// Streaming path of WindowMsd(unwrap=False): the trajectory arrives slab by slab (frame-major), and everything that is
+// a pass over the positions happens ON THE WAY IN:
+//   k_msd_slab_sums    per-frame mass-weighted sums of the slab (the centre of mass needs every atom of a frame before
+//                      any displacement can be wrapped: msd.py:235-237 precedes trajectory.py:285-303), deterministic;
+//   k_msd_slab_commit  centre-of-mass shift, displacement wrap (P8, the cell of the earlier frame), running sum along
+//                      time with a per-atom carry from the previous slab, and the transposition into the atom-major
+//                      store -- as three arrays x[Tp] | y[Tp] | z[Tp] per atom, which is the layout the window kernel
+//                      wants in shared memory, so its staging is one bulk copy.
+// The running sum starts from 0 instead of the first position (R'_k = R_k - R_0): every difference R_k - R_{k-m} is
+// unchanged, and the smaller magnitudes are what lets the window kernel use the autocorrelation form.
+//   k_msd_window_soa   |R_k - R_j|^2 = |R_k|^2 + |R_j|^2 - 2 R_k.R_j: the cross term costs 3 FMAs per frame pair (the
+//                      difference form 3 subtractions + 3 FMAs), the squares come from one prefix sum per atom.
+// =====================================================================================================================
+
+// partial[g][f*3 + c] = sum over the atoms of group g of w[a] * slab[f][a][c]
+__global__ void __launch_bounds__(256) k_msd_slab_sums(const double *__restrict__ slab, const double *__restrict__ w, int n, int count,
+                                                       double *__restrict__ partial) {
+    __shared__ double red[8][3];
+    const int f = blockIdx.x, g = blockIdx.y, groups = gridDim.y;
+    const int per = (n + groups - 1) / groups;
+    const int a_lo = g * per, a_hi = min(n, a_lo + per);
+    const double *src = slab + (size_t)f * n * 3;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int a = a_lo + threadIdx.x; a < a_hi; a += 256) {
+        const double m = w[a];
+        const double *p = src + 3 * (size_t)a;
+        ax = __fma_rn(m, p[0], ax); ay = __fma_rn(m, p[1], ay); az = __fma_rn(m, p[2], az);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = ax; red[warp][1] = ay; red[warp][2] = az; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x];
+        partial[(size_t)g * count * 3 + (size_t)f * 3 + threadIdx.x] = s;
+    }
+}
+
+#define COMMIT_A 64                       // atoms per block: 1 536-byte runs of every frame row
+#define COMMIT_FS 32                      // frames per round: 256-byte runs of every output row
+#define COMMIT_LD (3 * COMMIT_A + 1)      // odd row stride: the column reads of the write-out are conflict-free
+#define COMMIT_THREADS 384
+#define COMMIT_ITEMS ((COMMIT_FS * COMMIT_A + COMMIT_THREADS - 1) / COMMIT_THREADS)
+#define COMMIT_SMEM (sizeof(double) * (COMMIT_FS * COMMIT_LD + 6 * COMMIT_A))      // above the 48 KB static limit: opt-in
+
+// carry[a][6]: shifted position of the last committed frame, running sum up to it.
+// (A variant that kept the rows of round r+1 in flight with 8-byte cp.async copies into a second buffer was slower:
+// 12.1 instead of 10.3 ms per 100 000 atoms x 5 000 frames; the plain loads below already have 16 rows in flight per thread.)
+template <int CELL>      // 0 = one cell per frame, 1 = the same cell in every frame, 2 = the same orthorhombic cell
+__global__ void __launch_bounds__(COMMIT_THREADS, 3) k_msd_slab_commit(const double *__restrict__ slab, double *__restrict__ P,
+                                                                      const MsdGeom *__restrict__ geom, const double *__restrict__ com,
+                                                                      double *__restrict__ carry, int n, int Tp, int first, int count) {
+    extern __shared__ __align__(16) double commit_sm[];          // COMMIT_SMEM bytes
+    double *tile = commit_sm, *s_prev = tile + COMMIT_FS * COMMIT_LD, *s_run = s_prev + 3 * COMMIT_A;
+    const int a0 = blockIdx.x * COMMIT_A, na = min(COMMIT_A, n - a0), ncol = 3 * na;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < ncol; c += COMMIT_THREADS) {
+        const size_t at = (size_t)(a0 + c / 3) * 6 + (size_t)(c % 3);
+        s_prev[c] = first > 0 ? carry[at] : 0.0;
+        s_run[c] = first > 0 ? carry[at + 3] : 0.0;
+    }
+    MsdGeom g0;
+    if (CELL == 1) g0 = geom[0];
+    double i0 = 0.0, i4 = 0.0, i8 = 0.0, c0 = 0.0, c4 = 0.0, c8 = 0.0;
+    if (CELL == 2) { i0 = geom[0].inv[0]; i4 = geom[0].inv[4]; i8 = geom[0].inv[8]; c0 = geom[0].cell[0]; c4 = geom[0].cell[4]; c8 = geom[0].cell[8]; }
+    const int col = tid % (3 * COMMIT_A), row0 = tid / (3 * COMMIT_A), comp = col % 3;       // load mapping: my column is fixed
+    // item mapping of the wrap step: (frame row, atom) = (idx / 64, idx % 64), idx = tid + u * 384
+    for (int k0 = 0; k0 < count; k0 += COMMIT_FS) {
+        const int nr = min(COMMIT_FS, count - k0);
+        __syncthreads();                              // the previous round was written out (and the carry is in place)
+        // 1) rows of the slab, shifted by the centre of mass of their frame (translate(-cg), msd.py:237)
+        if (col < ncol) {
+            const double *src = slab + ((size_t)k0 * n + a0) * 3 + col;
+            const double *cm = com + 3 * (size_t)k0 + comp;
+            for (int r = row0; r < nr; r += COMMIT_THREADS / (3 * COMMIT_A))
+                tile[r * COMMIT_LD + col] = src[(size_t)r * n * 3] - cm[3 * r];
+        }
+        __syncthreads();
+        // 2) wrapped displacement of every (frame, atom) of the round, kept in registers until every position was read
+        double dx[COMMIT_ITEMS], dy[COMMIT_ITEMS], dz[COMMIT_ITEMS];
+#pragma unroll
+        for (int u = 0; u < COMMIT_ITEMS; ++u) {
+            const int idx = tid + u * COMMIT_THREADS, r = idx / COMMIT_A, aa = idx % COMMIT_A, k = first + k0 + r;
+            dx[u] = dy[u] = dz[u] = 0.0;
+            if (r < nr && aa < na && k > 0) {         // delta_0 = 0: the running sum is taken relative to the first frame
+                const double *q = tile + r * COMMIT_LD + 3 * aa;
+                const double *qp = r > 0 ? q - COMMIT_LD : s_prev + 3 * aa;
+                const double ex = q[0] - qp[0], ey = q[1] - qp[1], ez = q[2] - qp[2];
+                if (CELL == 2) wrap_disp_diag(i0, i4, i8, c0, c4, c8, ex, ey, ez, dx[u], dy[u], dz[u]);
+                else wrap_disp(CELL == 1 ? g0 : geom[k - 1], ex, ey, ez, dx[u], dy[u], dz[u]);     // cell of frame k-1 wraps k-1 -> k
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < ncol; c += COMMIT_THREADS) s_prev[c] = tile[(nr - 1) * COMMIT_LD + c];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < COMMIT_ITEMS; ++u) {
+            const int idx = tid + u * COMMIT_THREADS, r = idx / COMMIT_A, aa = idx % COMMIT_A;
+            if (r < nr && aa < na) {
+                double *q = tile + r * COMMIT_LD + 3 * aa;
+                q[0] = dx[u]; q[1] = dy[u]; q[2] = dz[u];
+            }
+        }
+        __syncthreads();
+        // 3) running sum along time, one thread per (atom, component), sequential like the reference's r_k += delta_k
+        if (tid < ncol) {
+            double run = s_run[tid];
+            for (int r = 0; r < nr; ++r) { run += tile[r * COMMIT_LD + tid]; tile[r * COMMIT_LD + tid] = run; }
+            s_run[tid] = run;
+        }
+        __syncthreads();
+        // 4) write-out: one warp per (atom, component), lanes = frames: 256-byte runs of the atom-major store
+        if (lane < nr) {
+            double *dst = P + (size_t)a0 * 3 * Tp + (size_t)(first + k0 + lane);
+            for (int c = warp; c < ncol; c += COMMIT_THREADS / 32) dst[(size_t)c * Tp] = tile[lane * COMMIT_LD + c];   // (a, comp) rows are consecutive: row a*3 + comp
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < ncol; c += COMMIT_THREADS) {
+        const size_t at = (size_t)(a0 + c / 3) * 6 + (size_t)(c % 3);
+        carry[at] = s_prev[c];
+        carry[at + 3] = s_run[c];
+    }
+}
+
+// One component of one atom at a time: |R_k - R_j|^2 and R_k . R_j are sums over x, y, z, so the block stages 8*Tp bytes
+// instead of 24*Tp, several blocks share an SM, and one block's bulk copy and barriers hide behind the others' tiles.
+#ifndef MSD_SOA_THREADS
+#define MSD_SOA_THREADS 256
+#endif
+#ifndef MSD_SOA_MIN_BLOCKS
+#define MSD_SOA_MIN_BLOCKS 3
+#endif
+#ifndef MSD_SOA_KB
+#define MSD_SOA_KB 8            // frames a thread keeps in registers per tile (4: 7.09, 6: 6.59, 8: 6.54 ms per 100 000 atoms x 5 000 frames)
+#endif
+
+// sm: one component of the series.  DOT: acc[w] += v_k * v_j, else acc[w] += (v_k - v_j)^2.
+// EDGE: the walk stops at the first partner before frame 1 (the reference starts at k = m + 1, msd.py:197).
+// (Walking the frames with pointer steps instead of b + i*delta, and advancing the task index without a division, measured
+// 6 % slower: 6.92 instead of 6.53 ms per 100 000 atoms x 5 000 frames.)
+template <int KB, int NWT, bool EDGE, bool DOT>
+__device__ __forceinline__ void msd_soa_tile(const double *__restrict__ sm, int b, int delta, int lag0, double (&acc)[NWT]) {
+    double kv[KB];
+#pragma unroll
+    for (int i = 0; i < KB; ++i) kv[i] = sm[b + i * delta];
+#pragma unroll
+    for (int u = -(KB - 1); u < NWT; ++u) {
+        const int j0 = b - lag0 - u * delta;
+        if (EDGE && j0 < 1) break;
+        const double jv = sm[j0];
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+            const int w = u + i;
+            if (w >= 0 && w < NWT) {
+                if (DOT) acc[w] = __fma_rn(kv[i], jv, acc[w]);
+                else { const double d = kv[i] - jv; acc[w] = __fma_rn(d, d, acc[w]); }
+            }
+        }
+    }
+}
+
+// P: prepared series, atom-major, three arrays of tp doubles per atom.  Window lengths 0, delta, 2 delta, ...
+// partial[block][2][S][nw]: [0] the pair sums (cross terms when DOT, squared differences otherwise), [1] when DOT the
+// sums of |R_k|^2 + |R_{k-m}|^2 over the same pairs; the caller forms [1] - 2 [0].
+template <int KB, int NWT, bool DOT>
+__global__ void __launch_bounds__(MSD_SOA_THREADS, MSD_SOA_MIN_BLOCKS) k_msd_window_soa(const double *__restrict__ P, const uint8_t *__restrict__ species,
+                                                                                      const int *__restrict__ perm, int n, int T,
+                                                                                      int tp, int delta, int nw, int ng, int S, double *__restrict__ partial) {
+    extern __shared__ __align__(16) double sm[];
+    double *s_acc = sm + (size_t)tp;                        // [S][nw]
+    double *s_ss = s_acc + (size_t)S * nw;                  // [S][nw]
+    double *s_red = s_ss + (size_t)S * nw;                  // [nwarp][NWT]
+    double *s_q = s_red + (size_t)MSD_AP_NWT_MAX * (MSD_SOA_THREADS / 32);      // [blockDim + 32]: exclusive prefix of the per-thread sums of squares
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int grp = warp % ng, wpg = nwarp / ng;            // my window group; warps per group
+    const int tg = (warp / ng) * 32 + lane, gs = wpg * 32;  // my index among the group's threads
+    for (int i = threadIdx.x; i < 2 * S * nw; i += blockDim.x) s_acc[i] = 0.0;      // s_acc and s_ss are adjacent
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+    const unsigned sm_addr = (unsigned)__cvta_generic_to_shared(sm);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    unsigned phase = 0;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int a_lo = blockIdx.x * per, a_hi = min(n, a_lo + per);
+    const int span = KB * delta;
+    const int nsr = (T - 1) / span;                         // full super-rows over k = 1 .. T-1
+    const int ntask = nsr * delta;
+    const int k_rem = 1 + nsr * span;                       // first frame of the remainder
+    const int C = ((T + (int)blockDim.x - 1) / (int)blockDim.x) | 1;     // frames per thread in the prefix of squares (odd: conflict-free)
+    const unsigned row_bytes = 8u * (unsigned)tp;
+    for (int w0 = 0; w0 < nw; w0 += ng * NWT) {
+        const int wlo = w0 + grp * NWT;                     // first window of my group in this pass
+        const bool mine = wlo < nw;
+        const int lag0 = wlo * delta;
+        const int lag_far = lag0 + (NWT - 1) * delta;       // the longest lag of my group
+        double acc[NWT];
+#pragma unroll
+        for (int w = 0; w < NWT; ++w) acc[w] = 0.0;
+        int cur_sp = -1;
+        for (int ai = a_lo; ai <= a_hi; ++ai) {
+            // the block's atoms are visited in species order (perm: a stable sort of [a_lo, a_hi) by species), so the
+            // register sums are reduced at most S times per pass instead of at every change along the atom order
+            const int a = ai < a_hi ? perm[ai] : -1;
+            const int sp = ai < a_hi ? (int)species[a] : -2;
+            if (sp != cur_sp) {
+                if (cur_sp >= 0) {                          // species changed (or done): reduce the register sums
+#pragma unroll
+                    for (int w = 0; w < NWT; ++w) {
+                        double v = acc[w];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                        if (lane == 0) s_red[warp * NWT + w] = v;
+                        acc[w] = 0.0;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < ng * NWT) {           // thread -> (group, window of the group); warps of a group in order
+                        const int g = threadIdx.x / NWT, w = threadIdx.x - g * NWT, wi = w0 + g * NWT + w;
+                        if (wi < nw) {
+                            double t = 0.0;
+                            for (int q = 0; q < wpg; ++q) t += s_red[(q * ng + g) * NWT + w];
+                            s_acc[cur_sp * nw + wi] += t;
+                        }
+                    }
+                    __syncthreads();
+                }
+                cur_sp = sp;
+            }
+            if (ai >= a_hi) break;
+            const char *rec = reinterpret_cast<const char *>(P + (size_t)a * 3 * tp);
+            for (int comp = 0; comp < 3; ++comp) {
+                __syncthreads();                            // everyone finished the previous component
+                if (threadIdx.x == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_expect_tx(mbar, row_bytes);
+                    const char *src = rec + (size_t)comp * row_bytes;
+                    for (unsigned o = 0; o < row_bytes; o += 32768u) bulk_g2s(sm_addr + o, src + o, min(32768u, row_bytes - o), mbar);
+                    mbar_wait(mbar, phase);
+                }
+                phase ^= 1u;
+                {                                           // pull what comes next into L2 while this component is worked on
+                    const char *nx = comp < 2 ? rec + (size_t)(comp + 1) * row_bytes
+                                              : (ai + 1 < a_hi ? reinterpret_cast<const char *>(P + (size_t)perm[ai + 1] * 3 * tp) : nullptr);
+                    if (nx)
+                        for (int i = threadIdx.x; i < (int)((row_bytes + 127u) >> 7); i += blockDim.x)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + ((size_t)i << 7)));
+                }
+                __syncthreads();
+                if (DOT && w0 == 0) {
+                    // Q(k) = sum_{j<=k} v_j^2 (v_0 = 0): per-thread sums over C consecutive frames, block-wide exclusive prefix,
+                    // then one thread per window adds  sum_{k=m+1}^{T-1} v_k^2 + sum_{j=1}^{T-1-m} v_j^2 = (Q(T-1) - Q(m)) + Q(T-1-m)
+                    const int k0 = threadIdx.x * C, k1 = min(T, k0 + C);
+                    double q = 0.0;
+                    for (int k = k0; k < k1; ++k) q = __fma_rn(sm[k], sm[k], q);
+                    const double iq = warp_incl_scan(q, lane);
+                    if (lane == 31) s_q[blockDim.x + warp] = iq;
+                    __syncthreads();
+                    const double tq = lane < nwarp ? s_q[blockDim.x + lane] : 0.0;
+                    const double wq = warp_incl_scan(tq, lane);
+                    s_q[threadIdx.x] = __shfl_sync(0xffffffffu, wq - tq, warp) + (iq - q);
+                    __syncthreads();
+                    for (int wi = threadIdx.x; wi < nw; wi += blockDim.x) {
+                        const int m = wi * delta;
+                        auto Q = [&](int k) {               // inclusive prefix at frame k
+                            const int t = k / C;
+                            double v = s_q[t];
+                            for (int j = t * C; j <= k; ++j) v = __fma_rn(sm[j], sm[j], v);
+                            return v;
+                        };
+                        if (wi > 0 && m < T - 1) s_ss[cur_sp * nw + wi] += (Q(T - 1) - Q(m)) + Q(T - 1 - m);
+                    }
+                }
+                if (mine) {
+                    for (int q = tg; q < ntask; q += gs) {
+                        const int s = q / delta, r = q - s * delta;
+                        const int b = 1 + s * span + r;
+                        if (b - lag_far >= 1) msd_soa_tile<KB, NWT, false, DOT>(sm, b, delta, lag0, acc);
+                        else msd_soa_tile<KB, NWT, true, DOT>(sm, b, delta, lag0, acc);
+                    }
+                    for (int k = k_rem + tg; k < T; k += gs) {
+                        if (k - lag_far >= 1) msd_soa_tile<1, NWT, false, DOT>(sm, k, delta, lag0, acc);
+                        else msd_soa_tile<1, NWT, true, DOT>(sm, k, delta, lag0, acc);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * S * nw; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * S * nw + i] = s_acc[i];
+}

@@ -7,12 +7,26 @@ struct MsdState {
     double *d_masses = nullptr;       // [n]
     uint8_t *d_species = nullptr;     // [n]
     double *d_com = nullptr;          // [T][3]
-    double *d_stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    double *d_stage[3] = {nullptr, nullptr, nullptr};      // staging slots of host slabs (three: two slabs may await their commit while the next one is copied)
+    cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
     int stage_frames = 0, next_stage = 0;
     bool have_com = false, prepared = false, consumed = false, fixed_cell = false, diag_cell = false;
     std::vector<double> cell;         // host copy [T][9]
     double mass_sum = 0.0;
+    // streaming path (amofb_msd_slab_*): prepared series, three arrays of Tp doubles per atom
+    int Tp = 0;                       // T rounded up to even (16-byte aligned rows)
+    bool soa = false;                 // d_P holds (or is being filled with) the prepared SoA series
+    int slab_next = 0;                // next frame the streaming path expects
+    struct PendingSlab {              // a slab whose sums were enqueued and that awaits its commit
+        const double *ptr = nullptr;  // device pointer
+        int first = 0, count = 0, slot = -1;
+        double *d_partial = nullptr, *d_out = nullptr, *h_out = nullptr;
+        cudaEvent_t ev = nullptr;     // the sums have landed in h_out
+        bool waited = false;
+    } pend[2];
+    int n_pend = 0;                   // FIFO: pend[0] is the oldest
+    int sums_next = 0;                // next frame slab_sums expects
+    double *d_carry = nullptr;        // [n][6]
 };
 
 static void msd_release(amofb_ctx *ctx) {
@@ -20,10 +34,14 @@ static void msd_release(amofb_ctx *ctx) {
     if (!p) return;
     cudaStreamSynchronize(ctx->s_copy);
     cudaStreamSynchronize(ctx->s_compute);
-    pool_put(ctx, p->d_P); pool_put(ctx, p->d_geom); pool_put(ctx, p->d_masses); pool_put(ctx, p->d_species); pool_put(ctx, p->d_com);
-    for (int i = 0; i < 2; ++i) {
+    pool_put(ctx, p->d_P); pool_put(ctx, p->d_geom); pool_put(ctx, p->d_masses); pool_put(ctx, p->d_species); pool_put(ctx, p->d_com); pool_put(ctx, p->d_carry);
+    for (int i = 0; i < 3; ++i) {
         pool_put(ctx, p->d_stage[i]);
         if (p->ev_stage[i]) cudaEventDestroy(p->ev_stage[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        pool_put(ctx, p->pend[i].d_partial); pool_put(ctx, p->pend[i].d_out); pool_put(ctx, p->pend[i].h_out);
+        if (p->pend[i].ev) cudaEventDestroy(p->pend[i].ev);
     }
     delete p;
     ctx->msd = nullptr;
@@ -42,6 +60,7 @@ extern "C" int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const 
     if (!p) return AMOFB_ERR_MEMORY;
     ctx->msd = p;
     p->T = n_frames; p->n = n_atoms; p->S = n_species;
+    p->Tp = (n_frames + 1) & ~1;
     p->cell.assign(cell, cell + 9 * (size_t)n_frames);
     std::vector<MsdGeom> geom((size_t)n_frames);
     int rc = AMOFB_OK;
@@ -61,16 +80,20 @@ extern "C" int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const 
     p->diag_cell = p->fixed_cell;
     for (int q = 0; q < 9 && p->diag_cell; ++q)
         if (q % 4 != 0 && (geom[0].cell[q] != 0.0 || geom[0].inv[q] != 0.0)) p->diag_cell = false;
-    if ((rc = dev_alloc(ctx, &p->d_P, (size_t)n_atoms * n_frames * 3))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_P, (size_t)n_atoms * p->Tp * 3))) return fail(rc);
+    if ((rc = dev_alloc(ctx, &p->d_carry, (size_t)n_atoms * 6))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_geom, (size_t)n_frames))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_masses, (size_t)n_atoms))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_species, (size_t)n_atoms))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_com, (size_t)n_frames * 3))) return fail(rc);
-    // staging: >= 32 frames per chunk when that stays below 1 GiB per slot, so the transpose writes long runs
+    // staging slots: a multiple of 32 frames (the rounds of the commit kernel, 256-byte output runs) when 32 frames stay
+    // below 1.5 GiB per slot, at most 256 frames
     size_t frame_bytes = sizeof(double) * 3 * (size_t)n_atoms;
-    long long sf = (long long)((1ull << 30) / frame_bytes);
-    p->stage_frames = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(sf, 256), n_frames));
-    for (int i = 0; i < 2; ++i) {
+    long long sf = (long long)((3ull << 29) / frame_bytes);
+    sf = std::min<long long>(sf, 256);
+    if (sf >= 32) sf -= sf % 32;
+    p->stage_frames = (int)std::max<long long>(1, std::min<long long>(sf, n_frames));
+    for (int i = 0; i < 3; ++i) {
         if ((rc = dev_alloc(ctx, &p->d_stage[i], (size_t)p->stage_frames * n_atoms * 3))) return fail(rc);
         cudaEventCreateWithFlags(&p->ev_stage[i], cudaEventDisableTiming);
     }
@@ -99,7 +122,7 @@ static void msd_transpose_launch(amofb_ctx *ctx, MsdState *p, const double *src,
 static int msd_load_impl(amofb_ctx *ctx, int first_frame, int count, const double *pos, bool on_device) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_load"));
-    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_load after the positions were transformed");
+    if (p->prepared || p->consumed || p->soa) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_load after the positions were transformed");
     if (first_frame < 0 || count < 0 || first_frame + (long long)count > p->T || (count > 0 && !pos))
         return amofb_fail(ctx, AMOFB_ERR_ARG, "frames [%d, %d) outside [0, %d)", first_frame, first_frame + count, p->T);
     p->have_com = false;
@@ -109,7 +132,7 @@ static int msd_load_impl(amofb_ctx *ctx, int first_frame, int count, const doubl
         const double *src = pos + fr * done;
         if (!on_device) {
             int sl = p->next_stage;
-            p->next_stage ^= 1;
+            p->next_stage = (p->next_stage + 1) % 3;
             CUDA_TRY(ctx, cudaEventSynchronize(p->ev_stage[sl]));   // the transpose that last read this slot is done
             CUDA_TRY(ctx, cudaMemcpyAsync(p->d_stage[sl], src, sizeof(double) * fr * nf, cudaMemcpyHostToDevice, ctx->s_copy));
             cudaEvent_t ev;
@@ -145,7 +168,7 @@ static int msd_scan_grid(amofb_ctx *ctx, int n) {
 extern "C" int amofb_msd_unwrap(amofb_ctx *ctx) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_unwrap"));
-    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_unwrap after the positions were transformed");
+    if (p->prepared || p->consumed || p->soa) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_unwrap after the positions were transformed");
     if (p->fixed_cell) k_msd_scan<false, true><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, nullptr, p->n, p->T);
     else k_msd_scan<false, false><<<msd_scan_grid(ctx, p->n), 32 * SCAN_WARPS, 0, ctx->s_compute>>>(p->d_P, p->d_geom, nullptr, p->n, p->T);
     ctx->launches += 1;
@@ -174,7 +197,7 @@ static int msd_frame_sums(amofb_ctx *ctx, MsdState *p, const double *d_w, double
 extern "C" int amofb_msd_com_sums(amofb_ctx *ctx, double *sums) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_com_sums"));
-    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_com_sums after the positions were transformed");
+    if (p->prepared || p->consumed || p->soa) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_com_sums after the positions were transformed");
     if (!sums) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
     AMOFB_TRY(msd_frame_sums<3>(ctx, p, p->d_masses, p->d_com));   // d_com temporarily holds the weighted sums
     std::vector<double> tmp((size_t)p->T * 3);
@@ -191,7 +214,7 @@ extern "C" int amofb_msd_com_sums(amofb_ctx *ctx, double *sums) {
 extern "C" int amofb_msd_set_com(amofb_ctx *ctx, const double *com) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_set_com"));
-    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_set_com after the positions were transformed");
+    if (p->prepared || p->consumed || p->soa) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_set_com after the positions were transformed");
     if (!com) return amofb_fail(ctx, AMOFB_ERR_ARG, "null centre of mass");
     CUDA_TRY(ctx, cudaMemcpy(p->d_com, com, sizeof(double) * 3 * (size_t)p->T, cudaMemcpyHostToDevice));
     p->have_com = true;
@@ -209,12 +232,25 @@ static int msd_prepare(amofb_ctx *ctx, MsdState *p) {
     return AMOFB_OK;
 }
 
+static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delta, double *sums);
+
 extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window, double *sums) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_window"));
     if (p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "positions were consumed by amofb_msd_direct");
     if (n_window < 0 || (n_window > 0 && (!window || !sums))) return amofb_fail(ctx, AMOFB_ERR_ARG, "bad window arguments");
     const int S = p->S;
+    if (p->soa) {
+        if (p->n_pend > 0 || p->slab_next != p->T) return amofb_fail(ctx, AMOFB_ERR_STATE, "the streaming path has committed %d of %d frames", p->slab_next, p->T);
+        if (n_window == 0) return AMOFB_OK;
+        int d = n_window >= 2 ? window[1] : 1;
+        bool ap = window[0] == 0 && d > 0;
+        for (int w = 2; w < n_window && ap; ++w) ap = (long long)window[w] == (long long)w * d;
+        if (!ap || 4LL * d >= p->T)
+            return amofb_fail(ctx, AMOFB_ERR_ARG, "the streaming path takes window lengths 0, D, 2D, ... with 4 D < n_frames; use amofb_msd_load for others");
+        nvtx_range rng("amofb_msd_window");
+        return msd_window_soa(ctx, p, n_window, d, sums);
+    }
     if (n_window == 0) {                                    // nothing to sum: only bring the trajectory into the prepared state
         if (!p->prepared) AMOFB_TRY(msd_prepare(ctx, p));
         return AMOFB_OK;
@@ -336,10 +372,235 @@ extern "C" int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window,
     return AMOFB_OK;
 }
 
+
+// ---- streaming path ---------------------------------------------------------------------------------------------
+extern "C" int amofb_msd_slab_frames(amofb_ctx *ctx, int *frames) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_slab_frames"));
+    if (!frames) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
+    *frames = p->stage_frames;
+    return AMOFB_OK;
+}
+
+// enqueue the copy (host slabs) and the mass sums of one slab; the result is fetched by msd_slab_sums_wait
+static int msd_slab_sums_begin_impl(amofb_ctx *ctx, int first_frame, int count, const double *pos, bool on_device) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_slab_sums"));
+    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_slab_sums after the positions were transformed");
+    if (p->n_pend >= 2) return amofb_fail(ctx, AMOFB_ERR_STATE, "two slabs already await amofb_msd_slab_commit");
+    if (count < 1 || !pos || first_frame != p->sums_next || first_frame + (long long)count > p->T)
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "slabs must cover the frames in order: expected first_frame %d, got [%d, %d) of %d", p->sums_next,
+                          first_frame, first_frame + count, p->T);
+    if (!on_device && count > p->stage_frames)
+        return amofb_fail(ctx, AMOFB_ERR_ARG, "a host slab holds at most %d frames (amofb_msd_slab_frames)", p->stage_frames);
+    p->soa = true;                    // from here on d_P is the prepared SoA store
+    const size_t fr = 3 * (size_t)p->n;
+    const double *src = pos;
+    int sl = -1;
+    nvtx_range rng("amofb_msd_slab_sums");
+    if (!on_device) {
+        sl = p->next_stage;
+        p->next_stage = (p->next_stage + 1) % 3;
+        CUDA_TRY(ctx, cudaEventSynchronize(p->ev_stage[sl]));   // the commit that last read this slot is done
+        CUDA_TRY(ctx, cudaMemcpyAsync(p->d_stage[sl], pos, sizeof(double) * fr * count, cudaMemcpyHostToDevice, ctx->s_copy));
+        cudaEvent_t ev;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventRecord(ev, ctx->s_copy));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_compute, ev, 0));
+        CUDA_TRY(ctx, cudaEventDestroy(ev));
+        src = p->d_stage[sl];
+    }
+    MsdState::PendingSlab &q = p->pend[p->n_pend];
+    const int groups = std::max(1, std::min(64, p->n / 4096));
+    pool_put(ctx, q.d_partial); pool_put(ctx, q.d_out); pool_put(ctx, q.h_out);
+    q.d_partial = q.d_out = q.h_out = nullptr;
+    AMOFB_TRY(dev_alloc(ctx, &q.d_partial, (size_t)groups * count * 3));
+    AMOFB_TRY(dev_alloc(ctx, &q.d_out, (size_t)count * 3));
+    AMOFB_TRY(pinned_alloc(ctx, &q.h_out, (size_t)count * 3));
+    if (!q.ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&q.ev, cudaEventDisableTiming));
+    k_msd_slab_sums<<<dim3(count, groups), 256, 0, ctx->s_compute>>>(src, p->d_masses, p->n, count, q.d_partial);
+    k_msd_sum_groups<<<std::max(1, std::min((count * 3 + 255) / 256, ctx->num_sms * 4)), 256, 0, ctx->s_compute>>>(q.d_partial, groups, count * 3, q.d_out);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(q.h_out, q.d_out, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, ctx->s_compute));
+    CUDA_TRY(ctx, cudaEventRecord(q.ev, ctx->s_compute));
+    q.ptr = src; q.first = first_frame; q.count = count; q.slot = sl; q.waited = false;
+    p->n_pend += 1;
+    p->sums_next = first_frame + count;
+    return AMOFB_OK;
+}
+
+// sums of the oldest slab whose sums have not been fetched yet
+static int msd_slab_sums_wait_impl(amofb_ctx *ctx, double *sums) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_slab_sums_wait"));
+    if (!sums) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
+    for (int i = 0; i < p->n_pend; ++i) {
+        MsdState::PendingSlab &q = p->pend[i];
+        if (q.waited) continue;
+        CUDA_TRY(ctx, cudaEventSynchronize(q.ev));
+        for (int k = 0; k < q.count; ++k) {
+            sums[4 * (size_t)k] = q.h_out[3 * (size_t)k];
+            sums[4 * (size_t)k + 1] = q.h_out[3 * (size_t)k + 1];
+            sums[4 * (size_t)k + 2] = q.h_out[3 * (size_t)k + 2];
+            sums[4 * (size_t)k + 3] = p->mass_sum;
+        }
+        q.waited = true;
+        return AMOFB_OK;
+    }
+    return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_slab_sums_wait without a slab whose sums are outstanding");
+}
+
+extern "C" int amofb_msd_slab_sums_begin(amofb_ctx *ctx, int first_frame, int count, const double *pos) {
+    return msd_slab_sums_begin_impl(ctx, first_frame, count, pos, false);
+}
+extern "C" int amofb_msd_slab_sums_begin_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device) {
+    return msd_slab_sums_begin_impl(ctx, first_frame, count, pos_device, true);
+}
+extern "C" int amofb_msd_slab_sums_wait(amofb_ctx *ctx, double *sums) { return msd_slab_sums_wait_impl(ctx, sums); }
+extern "C" int amofb_msd_slab_sums(amofb_ctx *ctx, int first_frame, int count, const double *pos, double *sums) {
+    AMOFB_TRY(msd_slab_sums_begin_impl(ctx, first_frame, count, pos, false));
+    return msd_slab_sums_wait_impl(ctx, sums);
+}
+extern "C" int amofb_msd_slab_sums_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device, double *sums) {
+    AMOFB_TRY(msd_slab_sums_begin_impl(ctx, first_frame, count, pos_device, true));
+    return msd_slab_sums_wait_impl(ctx, sums);
+}
+
+extern "C" int amofb_msd_slab_commit(amofb_ctx *ctx, const double *com) {
+    MsdState *p = nullptr;
+    AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_slab_commit"));
+    if (p->n_pend < 1) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_slab_commit before amofb_msd_slab_sums");
+    if (!p->pend[0].waited) return amofb_fail(ctx, AMOFB_ERR_STATE, "the sums of the oldest slab were never fetched");
+    if (!com) return amofb_fail(ctx, AMOFB_ERR_ARG, "null centre of mass");
+    nvtx_range rng("amofb_msd_slab_commit");
+    MsdState::PendingSlab q = p->pend[0];
+    const int first = q.first, count = q.count;
+    double *d_com = p->d_com + 3 * (size_t)first;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, ctx->s_compute));   // pageable: staged before return
+    const int blocks = (p->n + COMMIT_A - 1) / COMMIT_A;
+    const int cm = p->diag_cell ? 2 : (p->fixed_cell ? 1 : 0);
+    const void *kfn = cm == 2 ? (const void *)k_msd_slab_commit<2> : cm == 1 ? (const void *)k_msd_slab_commit<1> : (const void *)k_msd_slab_commit<0>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COMMIT_SMEM));
+    {
+        const double *a_slab = q.ptr; double *a_P = p->d_P; const MsdGeom *a_geom = p->d_geom; const double *a_com = d_com; double *a_carry = p->d_carry;
+        int a_n = p->n, a_tp = p->Tp, a_first = first, a_count = count;
+        void *kargs[] = {(void *)&a_slab, (void *)&a_P, (void *)&a_geom, (void *)&a_com, (void *)&a_carry, (void *)&a_n, (void *)&a_tp, (void *)&a_first, (void *)&a_count};
+        CUDA_TRY(ctx, cudaLaunchKernel(kfn, dim3(blocks), dim3(COMMIT_THREADS), kargs, COMMIT_SMEM, ctx->s_compute));
+    }
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (q.slot >= 0) CUDA_TRY(ctx, cudaEventRecord(p->ev_stage[q.slot], ctx->s_compute));
+    // pop the FIFO (the entries swap so that the buffers of the popped one are reused)
+    p->pend[0] = p->pend[1];
+    p->pend[1] = q;
+    p->pend[1].ptr = nullptr;
+    p->n_pend -= 1;
+    p->slab_next = first + count;
+    return AMOFB_OK;
+}
+
+// window sums from the prepared SoA store (lengths 0, D, 2D, ...): autocorrelation form first; a window whose result is
+// small against the squares it was taken from (loss of digits) sends the whole request through the difference form
+static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delta, double *sums) {
+    const int S = p->S;
+    int threads = MSD_SOA_THREADS, ap_ng = 1, ap_nwt = 13;
+    {
+        // groups of <= 13 window sums bound to warps: the shape that wastes the fewest thread slots
+        const int span = MSD_SOA_KB * ap_delta, nsr = (p->T - 1) / span;
+        const long long ntask = (long long)nsr * ap_delta, rem = (p->T - 1) - (long long)nsr * span;
+        const int nwarp = MSD_SOA_THREADS / 32;
+        const int force_ng = env_int("AMOFB_MSD_AP_NG", 0), force_nwt = env_int("AMOFB_MSD_AP_NWT", 0);
+        double best = -1.0;
+        for (int nwt = 5; nwt <= MSD_AP_NWT_MAX; nwt += 2) {
+            if (force_nwt > 0 && nwt != force_nwt) continue;
+            for (int ng = 1; ng <= nwarp; ng *= 2) {          // the warps split evenly over the groups
+                if (force_ng > 0 && ng != force_ng) continue;
+                if (ng > 1 && (ng - 1) * nwt >= n_window) break;
+                const int passes = (n_window + ng * nwt - 1) / (ng * nwt);
+                const int gs = 32 * (nwarp / ng);
+                const double slots = (double)((ntask + gs - 1) / gs) * MSD_SOA_KB + (double)((rem + gs - 1) / gs);
+                const double fill = ((double)ntask * MSD_SOA_KB + (double)rem) / (slots * gs);
+                const double balance = (double)n_window / ((double)passes * ng * nwt);
+                const double ppl = (double)(MSD_SOA_KB * nwt) / (double)(2 * MSD_SOA_KB + nwt - 1);      // pairs per shared-memory read
+                const double eff = fill * balance * std::min(1.0, ppl / 2.6) / passes;                  // every pass stages the atoms again
+                if (eff > best + 1e-9) { best = eff; ap_ng = ng; ap_nwt = nwt; }
+            }
+        }
+    }
+    if (env_int("AMOFB_MSD_DEBUG", 0)) fprintf(stderr, "[amofb msd] window kernel shape: %d sums per thread, %d groups, %d warps per group (%d threads)\n", ap_nwt, ap_ng, threads / 32 / ap_ng, threads);
+    const size_t smem = sizeof(double) * ((size_t)p->Tp + 2 * (size_t)S * n_window + (size_t)MSD_AP_NWT_MAX * (MSD_SOA_THREADS / 32) + MSD_SOA_THREADS + 32 + 8);
+    if (smem + 64 > (size_t)ctx->max_smem_optin) return amofb_fail(ctx, AMOFB_ERR_ARG, "%d frames and %d window lengths do not fit the shared-memory series buffer", p->T, n_window);
+    for (int form = env_int("AMOFB_MSD_NO_DOT", 0) ? 1 : 0; form < 2; ++form) {
+        const bool dot = form == 0;
+        const void *kfn = nullptr;
+#define AMOFB_SOA_KERNEL(NWT_) (dot ? (const void *)k_msd_window_soa<MSD_SOA_KB, NWT_, true> : (const void *)k_msd_window_soa<MSD_SOA_KB, NWT_, false>)
+        switch (ap_nwt) {
+            case 5: kfn = AMOFB_SOA_KERNEL(5); break;
+            case 7: kfn = AMOFB_SOA_KERNEL(7); break;
+            case 9: kfn = AMOFB_SOA_KERNEL(9); break;
+            case 11: kfn = AMOFB_SOA_KERNEL(11); break;
+            default: kfn = AMOFB_SOA_KERNEL(13); ap_nwt = 13; break;
+        }
+#undef AMOFB_SOA_KERNEL
+        int per_sm = 0;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+        if (per_sm < 1) return amofb_fail(ctx, AMOFB_ERR_CUDA, "window kernel does not fit on an SM");
+        const int grid = std::max(1, std::min(p->n, ctx->num_sms * per_sm));
+        double *d_partial = nullptr;
+        int *d_perm = nullptr;
+        AMOFB_TRY(dev_alloc(ctx, &d_partial, (size_t)grid * 2 * S * n_window));
+        if (int rc2 = dev_alloc(ctx, &d_perm, (size_t)p->n)) { pool_put(ctx, d_partial); return rc2; }
+        {
+            // every block visits its range of atoms in species order (counting sort per range)
+            std::vector<uint8_t> spec((size_t)p->n);
+            std::vector<int> perm((size_t)p->n);
+            cudaMemcpy(spec.data(), p->d_species, (size_t)p->n, cudaMemcpyDeviceToHost);
+            const int per = (p->n + grid - 1) / grid;
+            for (int lo = 0; lo < p->n; lo += per) {
+                const int hi = std::min(p->n, lo + per);
+                int at = lo;
+                for (int sp = 0; sp < S; ++sp)
+                    for (int a = lo; a < hi; ++a)
+                        if (spec[a] == sp) perm[at++] = a;
+            }
+            cudaMemcpy(d_perm, perm.data(), sizeof(int) * (size_t)p->n, cudaMemcpyHostToDevice);
+        }
+        std::vector<double> part((size_t)grid * 2 * S * n_window);
+        const double *a_P = p->d_P; const uint8_t *a_sp = p->d_species; const int *a_perm = d_perm;
+        int a_n = p->n, a_T = p->T, a_tp = p->Tp, a_S = S, a_nw = n_window, a_delta = ap_delta;
+        void *kargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_perm, (void *)&a_n, (void *)&a_T, (void *)&a_tp, (void *)&a_delta, (void *)&a_nw, (void *)&ap_ng, (void *)&a_S, (void *)&d_partial};
+        cudaError_t e = cudaLaunchKernel(kfn, dim3(grid), dim3(threads), kargs, smem, ctx->s_compute);
+        ctx->launches += 1;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, ctx->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
+        pool_put(ctx, d_partial);
+        pool_put(ctx, d_perm);
+        CUDA_TRY(ctx, e);
+        bool redo = false;
+        for (int i = 0; i < S * n_window; ++i) {
+            double c = 0.0, ss = 0.0;
+            for (int b = 0; b < grid; ++b) {                  // fixed order: deterministic
+                c += part[(size_t)b * 2 * S * n_window + i];
+                ss += part[(size_t)b * 2 * S * n_window + (size_t)S * n_window + i];
+            }
+            if (i % n_window == 0) { sums[i] = 0.0; continue; }            // m = 0: exactly zero (msd.py:197-204 with m = 0)
+            if (!dot) { sums[i] = c; continue; }
+            const double v = ss - 2.0 * c;
+            // the cross term and the squares each carry ~1e-16 of ss: keep 1e-13 of the result
+            if (ss > 500.0 * fabs(v)) redo = true;
+            sums[i] = v;
+        }
+        if (!redo) break;
+    }
+    return AMOFB_OK;
+}
+
 extern "C" int amofb_msd_direct(amofb_ctx *ctx, double *sums) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_direct"));
-    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_direct needs the untouched positions");
+    if (p->prepared || p->consumed || p->soa) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_direct needs the untouched positions");
     if (!sums) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
     for (int k = 0; k < p->T; ++k) {
         const double *c = p->cell.data() + 9 * (size_t)k;
@@ -373,7 +634,7 @@ extern "C" int amofb_msd_direct(amofb_ctx *ctx, double *sums) {
 extern "C" int amofb_msd_get_positions(amofb_ctx *ctx, double *pos) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_get_positions"));
-    if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "positions were already transformed in place");
+    if (p->prepared || p->consumed || p->soa) return amofb_fail(ctx, AMOFB_ERR_STATE, "positions were already transformed in place");
     if (!pos) return amofb_fail(ctx, AMOFB_ERR_ARG, "null output");
     const size_t fr = 3 * (size_t)p->n;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_copy));

@@ -182,30 +182,6 @@ struct TiledArgs {
     int max_tiles;
 };
 
-// ---- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier ----------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE_%=;\n"
-        "bra MBAR_WAIT_%=;\n"
-        "MBAR_DONE_%=:\n"
-        "}\n" :: "r"(mbar), "r"(parity) : "memory");
-}
-
 // shared-memory accesses through an explicit 32-bit shared address kept in a register: the compiler otherwise
 // re-derives the shared window base (S2R SR_CgaCtaId + LEA) inside the loops
 __device__ __forceinline__ void lds_xyz(unsigned addr, double &x, double &y, double &z) {

@@ -43,27 +43,59 @@ def _parallel_copy(dst, sources):
 
 
 class ArrayTrajectory:
-    """A trajectory stored as arrays: ``numbers[N]``, ``positions[T][N][3]``, ``cells[T][3][3]`` (or one [3][3])."""
+    """A trajectory stored as arrays: ``numbers[N]``, ``positions[T][N][3]``, ``cells[T][3][3]`` (or one [3][3]).
 
-    def __init__(self, numbers, positions, cells, masses=None, pinned=False):
+    A rank of a frame-sharded job may hold only ITS block of frames: ``positions`` then covers the frames
+    ``[first_frame, first_frame + len(positions))`` of a trajectory of ``n_frames`` frames (``cells`` always covers all of
+    them).  ``len()`` is the length of the whole trajectory, so the analyses shard it exactly as they shard a fully
+    resident one (:func:`frame_range`); indexing a frame that is not resident yields an Atoms that carries the atomic
+    numbers, masses and cell but NaN positions."""
+
+    def __init__(self, numbers, positions, cells, masses=None, pinned=False, first_frame=0, n_frames=None):
         self.pinned = bool(pinned)       # positions live in page-locked memory (Context.pinned_empty): copied as they are
         self.numbers = np.asarray(numbers, dtype=np.int64)
         self.positions = np.asarray(positions, dtype=np.float64)
         if self.positions.ndim != 3 or self.positions.shape[1:] != (len(self.numbers), 3):
             raise ValueError("positions must be [T][N][3]")
+        self.first_frame = int(first_frame)
+        self.n_frames = self.first_frame + self.positions.shape[0] if n_frames is None else int(n_frames)
+        if self.first_frame < 0 or self.first_frame + self.positions.shape[0] > self.n_frames:
+            raise ValueError("resident frames [%d, %d) do not fit a trajectory of %d frames"
+                             % (self.first_frame, self.first_frame + self.positions.shape[0], self.n_frames))
         cells = np.asarray(cells, dtype=np.float64)
         if cells.shape == (3, 3):
-            cells = np.broadcast_to(cells, (self.positions.shape[0], 3, 3))
-        self.cells = np.ascontiguousarray(cells).reshape(self.positions.shape[0], 3, 3)
+            cells = np.broadcast_to(cells, (self.n_frames, 3, 3))
+        self.cells = np.ascontiguousarray(cells).reshape(self.n_frames, 3, 3)
         self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)
 
     def __len__(self):
-        return self.positions.shape[0]
+        return self.n_frames
+
+    def resident(self, a, b):
+        return self.first_frame <= a and b <= self.first_frame + self.positions.shape[0]
+
+    def block(self, a, b):
+        """positions of the frames [a, b) (a view); they must be resident"""
+        if not self.resident(a, b):
+            raise IndexError("frames [%d, %d) are not resident (this rank holds [%d, %d))"
+                             % (a, b, self.first_frame, self.first_frame + self.positions.shape[0]))
+        return self.positions[a - self.first_frame:b - self.first_frame]
 
     def __getitem__(self, k):
         if isinstance(k, slice):
-            return ArrayTrajectory(self.numbers, self.positions[k], self.cells[k], self.masses, self.pinned)
-        a = Atoms(numbers=self.numbers, positions=self.positions[k], cell=self.cells[k], masses=self.masses)
+            a, b, step = k.indices(self.n_frames)
+            if step != 1:
+                raise IndexError("ArrayTrajectory slices must be contiguous")
+            return ArrayTrajectory(self.numbers, self.block(a, max(a, b)), self.cells[a:max(a, b)], self.masses, self.pinned)
+        k = int(k)
+        if k < 0:
+            k += self.n_frames
+        if not 0 <= k < self.n_frames:
+            raise IndexError(k)
+        if self.resident(k, k + 1):
+            a = Atoms(numbers=self.numbers, positions=self.positions[k - self.first_frame], cell=self.cells[k], masses=self.masses)
+        else:
+            a = Atoms(numbers=self.numbers, positions=np.full((len(self.numbers), 3), np.nan), cell=self.cells[k], masses=self.masses)
         a._parent = (self, k)
         return a
 
@@ -142,10 +174,10 @@ def iter_chunks(trajectory, lo, hi, backend, target_bytes=192 << 20):
     if is_array and (trajectory.pinned or ctx is None):
         for a in range(lo, hi, step):
             b = min(hi, a + step)
-            yield trajectory.positions[a:b], trajectory.cells[a:b]
+            yield trajectory.block(a, b), trajectory.cells[a:b]
         return
     if ctx is not None:
-        bufs = [ctx.scratch("frames%d" % i, (step, n, 3)) for i in range(2)]
+        bufs = [ctx.scratch("chunks%d" % i, (step, n, 3)) for i in range(2)]        # own names: msd._load_local stages too
     else:
         bufs = [np.empty((step, n, 3)) for _ in range(2)]
     which = 0
@@ -156,7 +188,8 @@ def iter_chunks(trajectory, lo, hi, backend, target_bytes=192 << 20):
         if ctx is not None:
             ctx.sync_copies()            # the copy that last read this buffer has finished
         if is_array:                     # pageable array: stage it ourselves, threaded, instead of the driver's bounce
-            _parallel_copy(buf, [trajectory.positions[k] for k in range(a, b)])
+            blk = trajectory.block(a, b)
+            _parallel_copy(buf, [blk[k] for k in range(b - a)])
             cells = trajectory.cells[a:b]
         else:
             frames_ = [trajectory[k] for k in range(a, b)]

@@ -47,10 +47,11 @@ def _load_local(session, trajectory, lo, hi, backend, target_bytes=64 << 20):
         whole = lo == 0 and hi == trajectory.positions.shape[1]
         for a in range(0, T, step):
             b = min(T, a + step)
-            session.load(a, trajectory.positions[a:b] if whole else trajectory.positions[a:b, lo:hi])
+            blk = trajectory.block(a, b)
+            session.load(a, blk if whole else blk[:, lo:hi])
         return
     ctx = getattr(backend, "ctx", None)
-    bufs = [ctx.scratch("frames%d" % i, (step, n, 3)) if ctx is not None else np.empty((step, n, 3)) for i in range(2)]
+    bufs = [ctx.scratch("msdload%d" % i, (step, n, 3)) if ctx is not None else np.empty((step, n, 3)) for i in range(2)]
     which = 0
     for a in range(0, T, step):
         b = min(T, a + step)
@@ -59,6 +60,56 @@ def _load_local(session, trajectory, lo, hi, backend, target_bytes=64 << 20):
         for k in range(a, b):
             buf[k - a] = frames._positions_of(trajectory[k])[lo:hi]
         session.load(a, buf[:b - a])       # returns once the copy has been issued and completed
+
+
+def _streamable(window, T):
+    """window lengths 0, D, 2D, ... with 4 D < T: what the streaming path of libamofb takes (amofb_msd_slab_*)"""
+    if len(window) < 2 or window[0] != 0 or window[1] <= 0:
+        return False
+    d = int(window[1])
+    return bool(np.all(window == np.arange(len(window)) * d)) and 4 * d < T
+
+
+def _stream_slabs(session, trajectory, lo, hi, backend, distributed):
+    """Feed the atoms [lo, hi) of every frame slab by slab; returns the centre of mass [T][3].
+
+    Two slabs are in flight: the sums of slab i+1 are enqueued before the (all-reduced) sums of slab i are turned into its
+    centre of mass, so the device always has work queued."""
+    T = len(trajectory)
+    n = hi - lo
+    step = max(1, min(T, session.slab_frames()))
+    com = np.empty((T, 3), dtype=np.float64)
+    is_array = isinstance(trajectory, frames.ArrayTrajectory)
+    whole = is_array and lo == 0 and hi == trajectory.positions.shape[1]
+    ctx = getattr(backend, "ctx", None)
+    bufs = None
+    if not whole:       # three staging buffers: a buffer is refilled only after its slab was committed
+        bufs = [ctx.scratch("msdslab%d" % i, (step, n, 3)) if ctx is not None else np.empty((step, n, 3)) for i in range(3)]
+    begun = []
+
+    def finish(a, b):
+        sums = _dist.allreduce_sum(session.slab_sums_wait(b - a), distributed)      # [count][4]: sum m*x, m*y, m*z, m
+        com[a:b] = sums[:, 0:3] / sums[:, 3:4]
+        session.slab_commit(com[a:b])
+
+    for i, a in enumerate(range(0, T, step)):
+        b = min(T, a + step)
+        if whole:
+            blk = trajectory.block(a, b)
+        else:
+            blk = bufs[i % 3][:b - a]
+            if is_array:
+                blk[...] = trajectory.block(a, b)[:, lo:hi]
+            else:
+                for k in range(a, b):
+                    blk[k - a] = frames._positions_of(trajectory[k])[lo:hi]
+        session.slab_sums_begin(a, blk)
+        begun.append((a, b))
+        if len(begun) == 2:
+            finish(*begun.pop(0))
+    while begun:
+        finish(*begun.pop(0))
+    return com
 
 
 def _open_session(trajectory, distributed, backend):
@@ -134,19 +185,31 @@ class WindowMsd(Msd):
         elements = list(set(trajectory[0].get_atomic_numbers()))          # column order, SURVEY.md Q3
         T = len(trajectory)
         backend, session, zs, spec, lo, hi = _open_session(trajectory, distributed, backend)
+        w = np.asarray(window, dtype=np.int64)
         with session:
-            _load_local(session, trajectory, lo, hi, backend)
             new_positions = None
-            if unwrap:
-                logger.info("Unwrap trajectory before computing msd")
-                session.unwrap()
-                if mutate and not _dist.active(distributed):
-                    new_positions = session.get_positions()
-            logger.info("Start computing msd at %s times on a trajectory of %s frames", len(window), T)
-            sums = _dist.allreduce_sum(session.com_sums(), distributed)      # [T][4]: sum m*x, m*y, m*z, m
-            com = sums[:, 0:3] / sums[:, 3:4]
-            session.set_com(com)
-            w = np.asarray(window, dtype=np.int64)
+            if not unwrap and _streamable(w, T) and hasattr(session, "slab_sums_begin"):
+                # every pass over the positions happens on the way in: mass sums per slab of frames, (all-reduced) centre of
+                # mass back, and the shift / wrap / running sum are fused into the transposition
+                logger.info("Start computing msd at %s times on a trajectory of %s frames", len(window), T)
+                com = _stream_slabs(session, trajectory, lo, hi, backend, distributed)
+            else:
+                _load_local(session, trajectory, lo, hi, backend)
+                if unwrap:
+                    logger.info("Unwrap trajectory before computing msd")
+                    session.unwrap()
+                    if mutate:
+                        new_positions = session.get_positions()
+                        if _dist.active(distributed):       # every rank mutates whole frames: gather the atom shards
+                            _, world = _dist.rank_world(distributed)
+                            n_all = len(spec)
+                            counts = [(n_all * (r + 1)) // world - (n_all * r) // world for r in range(world)]
+                            new_positions = np.ascontiguousarray(
+                                _dist.allgather_rows(np.ascontiguousarray(new_positions.transpose(1, 0, 2)), counts, distributed).transpose(1, 0, 2))
+                logger.info("Start computing msd at %s times on a trajectory of %s frames", len(window), T)
+                sums = _dist.allreduce_sum(session.com_sums(), distributed)      # [T][4]: sum m*x, m*y, m*z, m
+                com = sums[:, 0:3] / sums[:, 3:4]
+                session.set_com(com)
             raw = _dist.allreduce_sum(session.window(w), distributed) if len(w) else np.zeros((len(zs), 0))
         if mutate:
             self._mutate_frames(trajectory, com, new_positions)

@@ -186,6 +186,26 @@ int amofb_msd_load_device(amofb_ctx *ctx, int first_frame, int count, const doub
 int amofb_msd_unwrap(amofb_ctx *ctx);
 int amofb_msd_com_sums(amofb_ctx *ctx, double *sums);
 int amofb_msd_set_com(amofb_ctx *ctx, const double *com);
+ /* Streaming path for WindowMsd(unwrap=False): everything that is a pass over the positions happens on the way in.
+ * Per slab of consecutive frames, in frame order from frame 0 to n_frames:
+ *   slab_sums  : the slab (host double[count][n_atoms][3], count <= amofb_msd_slab_frames; the _device variant reads a
+ *                device pointer in place, any count, valid until the commit) -> sums double[count][4] =
+ *                (sum m*x, sum m*y, sum m*z, sum m) over the LOCAL atoms of each frame;
+ *   slab_commit: com double[count][3], the GLOBAL centre of mass of those frames (after the caller's all-reduce):
+ *                centre-of-mass shift (msd.py:235-237), displacement wrap with the cell of the earlier frame and running
+ *                sum (trajectory.py:285-303), written into the atom-major store.  Returns once enqueued.
+ * After the last commit amofb_msd_window takes window lengths 0, D, 2D, ... (what WindowMsd always asks for,
+ * msd.py:176-178); load / unwrap / com_sums / set_com / direct / get_positions belong to the other path. */
+int amofb_msd_slab_frames(amofb_ctx *ctx, int *frames);
+int amofb_msd_slab_sums(amofb_ctx *ctx, int first_frame, int count, const double *pos, double *sums);
+int amofb_msd_slab_sums_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device, double *sums);
+/* The same in two halves, so that the next slab's sums are already enqueued while the caller turns the previous
+ * slab's sums into a centre of mass: begin enqueues (at most two slabs may await their commit), wait returns the sums
+ * of the oldest slab whose sums were not fetched yet.  slab_sums == begin + wait. */
+int amofb_msd_slab_sums_begin(amofb_ctx *ctx, int first_frame, int count, const double *pos);
+int amofb_msd_slab_sums_begin_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device);
+int amofb_msd_slab_sums_wait(amofb_ctx *ctx, double *sums);
+int amofb_msd_slab_commit(amofb_ctx *ctx, const double *com);
 int amofb_msd_window(amofb_ctx *ctx, int n_window, const int *window, double *sums);
 int amofb_msd_direct(amofb_ctx *ctx, double *sums);
 int amofb_msd_get_positions(amofb_ctx *ctx, double *pos);

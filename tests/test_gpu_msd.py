@@ -187,3 +187,103 @@ def test_state_machine_errors(backend):
             s.window(np.array([0, 1], dtype=np.int32))          # no centre of mass yet
         with pytest.raises(ValueError):
             s.load(15, pos[:10])                                  # outside [0, T)
+
+
+# ---- streaming path (amofb_msd_slab_*): mass sums on the way in, shift + wrap + running sum fused into the transposition,
+# ---- autocorrelation window kernel --------------------------------------------------------------------------------
+def _gpu_stream(backend, pos, cells, spec, masses, S, window, slab, device=False):
+    T = len(pos)
+    com = np.empty((T, 3))
+    with backend.msd_open(T, masses, spec, S, cells) as s:
+        assert s.slab_frames() >= 1
+        for a in range(0, T, slab):
+            b = min(T, a + slab)
+            if device:
+                d = backend.ctx.device_alloc(pos[a:b].nbytes)
+                backend.ctx.h2d(d, pos[a:b])
+                sums = s.slab_sums(a, (d.value, b - a))
+            else:
+                sums = s.slab_sums(a, pos[a:b])
+            com[a:b] = sums[:, :3] / sums[:, 3:4]
+            s.slab_commit(com[a:b])
+            if device:
+                backend.ctx.sync()
+                backend.ctx.device_free(d)
+        raw = s.window(np.asarray(window, dtype=np.int32))
+    n_of = np.bincount(spec, minlength=S).astype(np.float64)
+    return raw / n_of[:, None] / (T - np.asarray(window, dtype=np.float64))[None, :], com
+
+
+@pytest.mark.parametrize("seed,T,n,tri,fixed,slab,delta,device", [
+    (1, 80, 50, False, False, 80, 3, False),       # one slab, a cell per frame
+    (2, 131, 33, True, False, 17, 5, False),       # odd T, slabs that are not multiples of the 32-frame rounds, carry across slabs
+    (3, 150, 70, True, True, 64, 4, True),         # one triclinic cell for every frame, device-resident slabs
+    (4, 97, 1, True, False, 10, 2, False),         # a single atom
+    (5, 200, 200, False, True, 33, 1, False),      # orthorhombic box along the axes (diagonal wrap), 100 window lengths
+    (6, 90, 129, True, False, 90, 7, True),        # atoms not a multiple of the 64-atom blocks
+])
+def test_streaming_path_matches_oracle(backend, seed, T, n, tri, fixed, slab, delta, device):
+    S = 3
+    pos, cells, spec, masses = _walk(500 + seed, T, n, tri)
+    if fixed:
+        cells[:] = cells[0]
+        f = np.einsum('kni,ij->knj', pos, np.linalg.inv(cells[0]))
+        pos = np.einsum('kni,ij->knj', f - np.floor(f), cells[0])
+    window = np.arange(0, T // 2, delta)
+    got, com = _gpu_stream(backend, pos, cells, spec, masses, S, window, slab, device)
+    want, _ = orc.msd_window(pos, cells, masses, spec, S, window)
+    present = np.bincount(spec, minlength=S) > 0
+    assert np.all(got[present][:, 0] == 0.0)
+    np.testing.assert_allclose(got[present], want[present], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(com, (masses[None, :, None] * pos).sum(axis=1) / masses.sum(), rtol=1e-13, atol=1e-13)
+
+
+def test_streaming_forms_agree_and_fall_back(backend, monkeypatch):
+    """The autocorrelation form must agree with the difference form, and a request whose windows are small against the
+    squares they are taken from (ballistic drift, lag 1) must come out right all the same (the library re-runs it in the
+    difference form)."""
+    S, T, n = 2, 400, 40
+    pos, cells, spec, masses = _walk(71, T, n, True, size=40.0, step=0.05, wrapped=False, nspec=S)
+    window = np.arange(0, T // 2, 10)
+    dot, _ = _gpu_stream(backend, pos, cells, spec, masses, S, window, 128)
+    monkeypatch.setenv("AMOFB_MSD_NO_DOT", "1")
+    diff, _ = _gpu_stream(backend, pos, cells, spec, masses, S, window, 128)
+    monkeypatch.delenv("AMOFB_MSD_NO_DOT")
+    want, _ = orc.msd_window(pos, cells, masses, spec, S, window)
+    np.testing.assert_allclose(dot, want, rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(diff, want, rtol=RTOL, atol=1e-13)
+    # two species moving against each other at constant velocity (the centre of mass stays put), tiny jitter:
+    # |R_k|^2 grows like k^2 while MSD(1) stays v^2
+    rng = np.random.default_rng(3)
+    vel = np.where(spec[:, None] == 0, 1.0, -1.0) * np.array([0.01, 0.02, -0.015]) / masses[:, None]
+    pos = pos[0][None] + np.arange(T)[:, None, None] * vel[None] + rng.normal(scale=1e-4, size=(T, n, 3))
+    window = np.arange(0, T // 2, 1)
+    got, _ = _gpu_stream(backend, pos, cells, spec, masses, S, window, 256)
+    want, _ = orc.msd_window(pos, cells, masses, spec, S, window)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-15)
+
+
+def test_streaming_state_machine(backend):
+    pos, cells, spec, masses = _walk(31, 40, 12, False)
+    with backend.msd_open(len(pos), masses, spec, 3, cells) as s:
+        with pytest.raises(ValueError):
+            s.slab_sums(5, pos[5:10])                             # slabs come in frame order
+        sums = s.slab_sums(0, pos[:16])
+        with pytest.raises(RuntimeError):
+            s.load(0, pos)                                        # the two paths do not mix
+        s.slab_sums_begin(16, pos[16:30])                         # two slabs may await their commit ...
+        with pytest.raises(RuntimeError):
+            s.slab_sums_begin(30, pos[30:])                       # ... a third may not
+        s.slab_commit(sums[:, :3] / sums[:, 3:4])
+        with pytest.raises(RuntimeError):
+            s.window(np.array([0, 2, 4], dtype=np.int32))         # 24 frames are still missing
+        with pytest.raises(RuntimeError):
+            s.slab_commit(sums[:14, :3])                          # the sums of the oldest slab were never fetched
+        sums = s.slab_sums_wait(14)
+        s.slab_commit(sums[:, :3] / sums[:, 3:4])
+        sums = s.slab_sums(30, pos[30:])
+        s.slab_commit(sums[:, :3] / sums[:, 3:4])
+        with pytest.raises(ValueError):
+            s.window(np.array([0, 2, 5], dtype=np.int32))         # not an arithmetic progression: the other path's job
+        raw = s.window(np.array([0, 2, 4, 6], dtype=np.int32))
+    assert raw.shape == (3, 4) and np.all(raw[:, 0] == 0.0)
