@@ -281,8 +281,10 @@ struct Batcher {
     size_t cells_per_frame = 0;
     double rcut = 0.0;
     int cell_div = 1;
+    double cell_widen = 1.0;             // cells this much wider than rcut / cell_div (bond angles on species-filtered frames)
     uint8_t *d_species = nullptr;
     uint8_t *d_species_keep = nullptr;   // optional species filter of the cell list (bond angles)
+    int *d_keep_idx = nullptr;           // with the filter: original indices of the atoms that pass it
     int n_keep = 0;                      // atoms per frame that pass it (= n_atoms without a filter)
     bool want_orig = false;              // keep the original index of every sorted atom
     BatchSlot slot[2];
@@ -301,19 +303,22 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         s = BatchSlot();
     }
-    pool_put(ctx, b.d_species); pool_put(ctx, b.d_species_keep);
-    b.d_species = nullptr; b.d_species_keep = nullptr;
+    pool_put(ctx, b.d_species); pool_put(ctx, b.d_species_keep); pool_put(ctx, b.d_keep_idx);
+    b.d_species = nullptr; b.d_species_keep = nullptr; b.d_keep_idx = nullptr;
 }
 
+// n_work: atoms per frame that enter the cell list (< n_atoms under a species filter): the batch is sized by the work, the raw
+// frames of a batch are bounded by 1 GiB
 static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *species, double rcut, int cell_div,
-                        int per_frame_out, int max_frames = 0) {
+                        int per_frame_out, int max_frames = 0, int n_work = -1) {
     b.n_atoms = n_atoms;
     b.n_keep = n_atoms;
     b.rcut = rcut;
     b.cell_div = cell_div;
     b.per_frame_out = per_frame_out;
     long long target = env_int("AMOFB_BATCH_ATOMS", 1 << 22);     // 4 Mi atoms per batch: measured +22 % (BAD), +3 % (RDF) over 1 Mi
-    long long cap = target / std::max(n_atoms, 1);
+    long long cap = target / std::max(n_work > 0 ? n_work : n_atoms, 1);
+    cap = std::min<long long>(cap, (1ll << 30) / (24ll * std::max(n_atoms, 1)));
     b.cap_frames = (int)std::min<long long>(std::max<long long>(cap, 1), 8192);
     if (max_frames > 0 && b.cap_frames > max_frames) b.cap_frames = max_frames;
     b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0) + 1;
@@ -341,6 +346,20 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
     return AMOFB_OK;
 }
 
+// species filter of the cell list: atoms whose species has keep[] == 0 never enter it
+static int batcher_set_filter(amofb_ctx *ctx, Batcher &b, const uint8_t *species, const uint8_t *keep) {
+    std::vector<int> idx;
+    idx.reserve((size_t)b.n_atoms);
+    for (int i = 0; i < b.n_atoms; ++i)
+        if (keep[species[i]]) idx.push_back(i);
+    b.n_keep = (int)idx.size();
+    AMOFB_TRY(dev_alloc(ctx, &b.d_species_keep, (size_t)AMOFB_MAX_SPECIES));
+    CUDA_TRY(ctx, cudaMemcpy(b.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice));
+    AMOFB_TRY(dev_alloc(ctx, &b.d_keep_idx, idx.size() + 1));
+    if (!idx.empty()) CUDA_TRY(ctx, cudaMemcpy(b.d_keep_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    return AMOFB_OK;
+}
+
 // wait for the slot's batch and move its per-frame outputs to out_all
 static int batcher_harvest(amofb_ctx *ctx, Batcher &b, BatchSlot &s) {
     if (s.frames == 0) return AMOFB_OK;
@@ -365,7 +384,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     int cs_off = 0;
     for (int f = 0; f < nf; ++f) {
         FrameGeom &g = s.h_geom[f];
-        if (!host_fill_geom(g, cell + 9 * (size_t)f, b.rcut, b.cell_div, b.n_atoms))
+        if (!host_fill_geom(g, cell + 9 * (size_t)f, b.rcut, b.cell_div, b.n_keep, b.cell_widen))
             return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %lld: singular cell or cell far smaller than the cutoff %g",
                               (long long)(b.frames_seen + f), b.rcut);
         g.cs_off = cs_off;
@@ -390,10 +409,12 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.cell_count = s.d_cell_count; pa.cell_start = s.d_cell_start; pa.cid = s.d_cid; pa.rank = s.d_rank;
     pa.sorted = s.d_sorted; pa.n_atoms = b.n_atoms; pa.n_frames = nf;
     pa.species_keep = b.d_species_keep;
+    pa.keep_idx = b.d_keep_idx;
+    pa.n_keep = b.n_keep;
     pa.orig = s.d_orig;
     pa.wraps = s.d_wraps;
     pa.slot = nullptr;
-    long long total = (long long)nf * b.n_atoms;
+    long long total = (long long)nf * (b.d_keep_idx ? b.n_keep : b.n_atoms);
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;
     if (total > 0) {
@@ -580,11 +601,7 @@ extern "C" int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, cons
         for (int x = 0; x < S; ++x)
             for (int y = 0; y < S; ++y)
                 if (cn_cutoff[x * S + y] > 0.0) keep[x] = 1;
-        int n_keep = 0;
-        for (int i = 0; i < n_atoms; ++i) n_keep += keep[species[i]];
-        p->bt.n_keep = n_keep;
-        if ((rc = dev_alloc(ctx, &p->bt.d_species_keep, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
-        cudaMemcpy(p->bt.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice);
+        if ((rc = batcher_set_filter(ctx, p->bt, species, keep))) return fail(rc);
     }
     if ((rc = dev_alloc(ctx, &p->d_edge2, edge2.size()))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);

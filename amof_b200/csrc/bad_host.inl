@@ -9,6 +9,13 @@ struct BadState {
     int2 *d_triples = nullptr;
     unsigned long long *d_hist = nullptr, *d_dropped = nullptr;
     int *d_flags = nullptr;
+    BadNb *d_pool = nullptr;          // unit vectors of the neighbours of every centre of a batch
+    BadCentre *d_centres = nullptr;
+    unsigned *d_counters = nullptr;   // [0] centres, [1] pool entries
+    unsigned long long *d_centre_mask = nullptr;
+    unsigned pool_cap = 0;
+    int n_slots = 0, tthr_smem = 0, angle_grid = 0;
+    size_t angle_smem = 0;
     unsigned long long centre_mask[AMOFB_MAX_SPECIES];
 };
 
@@ -20,6 +27,7 @@ static void bad_release(amofb_ctx *ctx) {
     batcher_release(ctx, p->bt);
     pool_put(ctx, p->d_cnthr2); pool_put(ctx, p->d_tthr); pool_put(ctx, p->d_keyidx); pool_put(ctx, p->d_triples);
     pool_put(ctx, p->d_hist); pool_put(ctx, p->d_dropped); pool_put(ctx, p->d_flags);
+    pool_put(ctx, p->d_pool); pool_put(ctx, p->d_centres); pool_put(ctx, p->d_counters); pool_put(ctx, p->d_centre_mask);
     delete p;
     ctx->bad = nullptr;
 }
@@ -132,7 +140,21 @@ extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const
     double rcut = cut_max > 0.0 ? cut_max : 1e-3;
     int cell_div = env_int("AMOFB_BAD_CELL_DIV", 1);
     if (cell_div < 1) cell_div = 1;
-    if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, 0))) return fail(rc);
+    {
+        // cell width in cutoffs (measured on C4: 1.0 -> 3.99, 1.25 -> 4.4, 1.5 -> 4.71 us per frame): the filtered frames are sparse (0.3 atoms per cutoff-wide cell on the ZIF 'Zn-N'
+        // analysis), wider cells mean a third of the cells to count, scan and look up, for a few more distance evaluations
+        const char *w = getenv("AMOFB_BAD_CELL_WIDEN");
+        p->bt.cell_widen = w && *w ? atof(w) : 1.0;
+        if (!(p->bt.cell_widen >= 1.0)) p->bt.cell_widen = 1.0;
+    }
+    uint8_t keep_pre[AMOFB_MAX_SPECIES];
+    memset(keep_pre, 0, sizeof keep_pre);
+    for (int x = 0; x < S; ++x)
+        for (int y = 0; y < S; ++y)
+            if (cutoff[x * S + y] > 0.0) keep_pre[x] = 1;
+    int n_work = 0;
+    for (int i = 0; i < n_atoms; ++i) n_work += keep_pre[species[i]];
+    if ((rc = batcher_init(ctx, p->bt, n_atoms, species, rcut, cell_div, 0, 0, n_work))) return fail(rc);
     {   // species filter: an atom whose species has no positive cutoff with any species can neither be a centre with
         // neighbours nor a neighbour, so it never enters the cell list (ZIF-4 'Zn-N': 71 % of the atoms drop out)
         uint8_t keep[AMOFB_MAX_SPECIES];
@@ -140,11 +162,7 @@ extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const
         for (int x = 0; x < S; ++x)
             for (int y = 0; y < S; ++y)
                 if (cutoff[x * S + y] > 0.0) keep[x] = 1;
-        int n_keep = 0;
-        for (int i = 0; i < n_atoms; ++i) n_keep += keep[species[i]];
-        p->bt.n_keep = n_keep;
-        if ((rc = dev_alloc(ctx, &p->bt.d_species_keep, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
-        cudaMemcpy(p->bt.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice);
+        if ((rc = batcher_set_filter(ctx, p->bt, species, keep))) return fail(rc);
     }
     const size_t hist_n = (size_t)n_triples * (AMOFB_BAD_MAX_CN + 1) * nbins;
     if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
@@ -154,6 +172,28 @@ extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const
     if ((rc = dev_alloc(ctx, &p->d_hist, hist_n))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_dropped, (size_t)n_triples))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_flags, 1))) return fail(rc);
+    {
+        // neighbour pool of one batch: 16 neighbours per filtered atom, at most 512 MB (an overflow is reported, not dropped)
+        const size_t want = (size_t)std::max(p->bt.n_keep, 1) * (size_t)p->bt.cap_frames * 16;
+        p->pool_cap = (unsigned)std::min<size_t>(std::max<size_t>(want, 4096), (size_t)16 << 20);
+        if ((rc = dev_alloc(ctx, &p->d_pool, (size_t)p->pool_cap))) return fail(rc);
+        if ((rc = dev_alloc(ctx, &p->d_centres, (size_t)std::max(p->bt.n_keep, 1) * (size_t)p->bt.cap_frames))) return fail(rc);
+        if ((rc = dev_alloc(ctx, &p->d_counters, 2))) return fail(rc);
+        if ((rc = dev_alloc(ctx, &p->d_centre_mask, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
+        cudaMemcpy(p->d_centre_mask, p->centre_mask, sizeof p->centre_mask, cudaMemcpyHostToDevice);
+        // shared memory of the angle kernel: threshold table + as many histogram rows as fit (two blocks per SM)
+        const size_t budget = ((size_t)ctx->max_smem_optin + 1024) / 2 - 1024 - 256;
+        const size_t tab = sizeof(double) * ((size_t)nbins + 2), row = sizeof(uint32_t) * (size_t)nbins;
+        p->tthr_smem = tab <= budget ? 1 : 0;
+        size_t left = budget - (p->tthr_smem ? tab : 0);
+        p->n_slots = (int)std::min<size_t>(BAD_SLOTS, left / row);
+        p->angle_smem = (p->tthr_smem ? tab : 0) + row * (size_t)p->n_slots;
+        cudaError_t e1 = cudaFuncSetAttribute(k_bad_angles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->angle_smem);
+        int per_sm = 0;
+        if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bad_angles, 256, p->angle_smem);
+        if (e1 != cudaSuccess || per_sm < 1) { amofb_fail(ctx, AMOFB_ERR_CUDA, "bad_begin: angle kernel does not fit on an SM"); return fail(AMOFB_ERR_CUDA); }
+        p->angle_grid = ctx->num_sms * per_sm;
+    }
     cudaMemcpy(p->d_cnthr2, cnthr.data(), sizeof(double) * cnthr.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_tthr, tthr.data(), sizeof(double) * tthr.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_keyidx, keyidx.data(), sizeof(uint16_t) * keyidx.size(), cudaMemcpyHostToDevice);
@@ -196,14 +236,18 @@ static int bad_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool o
         a.cn_thr2 = p->d_cnthr2; a.keyidx = p->d_keyidx; a.triples = p->d_triples; a.tthr = p->d_tthr;
         a.hist = p->d_hist; a.dropped = p->d_dropped; a.flags = p->d_flags;
         a.n_keep = b.n_keep;
-        memcpy(a.centre_mask, p->centre_mask, sizeof a.centre_mask);
+        a.centre_mask = p->d_centre_mask;
         a.r2search = p->r2search; a.inv_dtheta_f = (float)(1.0 / p->dtheta);
         a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys;
         a.n_triples = p->n_triples; a.nbins = p->nbins;
+        a.pool = p->d_pool; a.centres = p->d_centres; a.counters = p->d_counters; a.pool_cap = p->pool_cap;
+        a.n_slots = p->n_slots; a.tthr_smem = p->tthr_smem;
         long long total = (long long)nf * b.n_keep;
         if (total > 0) {
-            k_bad<<<(unsigned)((total + 127) / 128), 128, 0, ctx->s_compute>>>(a);   // one thread per atom of the filtered, cell-sorted frames
-            ctx->launches += 1;
+            CUDA_TRY(ctx, cudaMemsetAsync(p->d_counters, 0, sizeof(unsigned) * 2, ctx->s_compute));
+            k_bad_search<<<(unsigned)((total + 127) / 128), 128, 0, ctx->s_compute>>>(a);   // one thread per atom of the filtered, cell-sorted frames
+            k_bad_angles<<<p->angle_grid, 256, p->angle_smem, ctx->s_compute>>>(a);         // one thread per centre found
+            ctx->launches += 2;
             CUDA_TRY(ctx, cudaGetLastError());
         }
         AMOFB_TRY(batcher_commit(ctx, b, *s, nf));
@@ -231,6 +275,7 @@ extern "C" int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *droppe
         CUDA_TRY(ctx, cudaMemcpy(&flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
         if (flags & 1) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "a centre has more than %d neighbours under the cutoffs", BAD_NB_MAX);
         if (flags & 2) return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "a centre has more than %d B-neighbours", AMOFB_BAD_MAX_CN);
+        if (flags & 4) return amofb_fail(ctx, AMOFB_ERR_MEMORY, "neighbour pool of a batch overflowed (%u entries); rerun with a smaller AMOFB_BATCH_ATOMS", p->pool_cap);
         const size_t hist_n = (size_t)p->n_triples * (AMOFB_BAD_MAX_CN + 1) * p->nbins;
         if (hist) CUDA_TRY(ctx, cudaMemcpy(hist, p->d_hist, sizeof(uint64_t) * hist_n, cudaMemcpyDeviceToHost));
         if (dropped) CUDA_TRY(ctx, cudaMemcpy(dropped, p->d_dropped, sizeof(uint64_t) * p->n_triples, cudaMemcpyDeviceToHost));

@@ -154,7 +154,8 @@ static inline void host_cell_heights(const double *inv, double *h) {
 //   cells of width >= rcut*(1+1e-9)/cell_div along every perpendicular direction, so a stencil of
 //   half-width m_k = ceil(rcut*(1+1e-9)/w_k) cells provably covers every pair within rcut even though
 //   atoms sit in their cell only up to fp rounding.
-static inline bool host_fill_geom(FrameGeom &g, const double *cell, double rcut, int cell_div, int n_atoms) {
+//   widen > 1 makes the cells that much wider than rcut/cell_div (sparse, species-filtered frames: fewer, fuller cells)
+static inline bool host_fill_geom(FrameGeom &g, const double *cell, double rcut, int cell_div, int n_atoms, double widen = 1.0) {
     memcpy(g.cell, cell, sizeof(double) * 9);
     if (!host_cell_inverse(cell, g.inv)) return false;
     double h[3];
@@ -162,7 +163,7 @@ static inline bool host_fill_geom(FrameGeom &g, const double *cell, double rcut,
     double rpad = rcut * (1.0 + 1e-9) + 1e-300;
     double total = 1.0;
     for (int k = 0; k < 3; ++k) {
-        double n = floor(h[k] * cell_div / rpad);
+        double n = floor(h[k] * cell_div / (rpad * (widen > 1.0 ? widen : 1.0)));
         if (!(n >= 1.0)) n = 1.0;
         if (n > 1024.0) n = 1024.0;
         g.nc[k] = (int)n;

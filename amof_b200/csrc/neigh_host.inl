@@ -80,11 +80,7 @@ extern "C" int amofb_neigh_count(amofb_ctx *ctx, int n_atoms, int n_species, con
         for (int x = 0; x < S; ++x)
             for (int y = 0; y < S; ++y)
                 if (cutoff[x * S + y] > 0.0) keep[x] = 1;
-        int n_keep = 0;
-        for (int i = 0; i < n_atoms; ++i) n_keep += keep[species[i]];
-        p->bt.n_keep = n_keep;
-        if ((rc = dev_alloc(ctx, &p->bt.d_species_keep, (size_t)AMOFB_MAX_SPECIES))) return fail(rc);
-        cudaMemcpy(p->bt.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice);
+        if ((rc = batcher_set_filter(ctx, p->bt, species, keep))) return fail(rc);
     }
     if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
     if ((rc = dev_alloc(ctx, &p->d_keyidx, keyidx.size()))) return fail(rc);

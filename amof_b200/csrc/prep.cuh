@@ -37,6 +37,8 @@ struct PrepArgs {
     // optional filter (bond angles): only atoms with species_keep[species] != 0 enter the cell list; the others can
     // neither be a centre nor a neighbour under the cutoff matrix, so the sorted frame holds cell_start[ncell] atoms
     const uint8_t *species_keep;   // [n_species] or nullptr
+    const int *keep_idx;           // with the filter: [n_keep] original indices of the atoms that pass it (the kernels then run
+    int n_keep;                    //   over n_frames * n_keep items instead of testing every atom of every frame)
     uint32_t *orig;                // optional [F*N]: original atom index of every sorted atom (explicit neighbour lists)
     int *wraps;                    // optional [F*N][3]: cell translations removed from every sorted atom by P2
     uint32_t *slot;                // optional [F*N]: position of every atom in its frame's sorted order (pair lists)
@@ -65,15 +67,18 @@ __device__ __forceinline__ void wrap_atom(const FrameGeom &g, const double *__re
 }
 
 __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
-    long long total = (long long)a.n_frames * a.n_atoms;
+    const int per = a.keep_idx ? a.n_keep : a.n_atoms;              // items per frame
+    long long total = (long long)a.n_frames * per;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int f = (int)(idx / a.n_atoms);
-        if (a.species_keep && !a.species_keep[a.species[idx - (long long)f * a.n_atoms]]) { a.cid[idx] = 0xffffffffu; continue; }
+        int f = (int)(idx / per);
+        int i = (int)(idx - (long long)f * per);
+        if (a.keep_idx) i = a.keep_idx[i];
+        else if (a.species_keep && !a.species_keep[a.species[i]]) { a.cid[idx] = 0xffffffffu; continue; }
         const FrameGeom &g = a.geom[f];
         double pw[3];
         int c[3];
-        wrap_atom(g, a.raw + 3 * idx, pw, c);
+        wrap_atom(g, a.raw + 3 * ((long long)f * a.n_atoms + i), pw, c);
         uint32_t cid = (uint32_t)((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
         a.cid[idx] = cid;
         a.rank[idx] = atomicAdd(&a.cell_count[g.cs_off + cid], 1u);
@@ -145,16 +150,18 @@ __global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
-    long long total = (long long)a.n_frames * a.n_atoms;
+    const int per = a.keep_idx ? a.n_keep : a.n_atoms;
+    long long total = (long long)a.n_frames * per;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int f = (int)(idx / a.n_atoms);
-        int i = (int)(idx - (long long)f * a.n_atoms);
+        int f = (int)(idx / per);
+        int i = (int)(idx - (long long)f * per);
+        if (a.keep_idx) i = a.keep_idx[i];
         if (a.cid[idx] == 0xffffffffu) continue;          // filtered out by species_keep
         const FrameGeom &g = a.geom[f];
         double pw[3];
         int c[3], wn[3];
-        wrap_atom(g, a.raw + 3 * idx, pw, c, wn);
+        wrap_atom(g, a.raw + 3 * ((long long)f * a.n_atoms + i), pw, c, wn);
         uint32_t dst = a.cell_start[g.cs_off + a.cid[idx]] + a.rank[idx];
         SAtom s;
         s.x = pw[0]; s.y = pw[1]; s.z = pw[2];
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         s.s = (long long)a.species[i] | ((long long)c[0] << 8) | ((long long)c[1] << 20) | ((long long)c[2] << 32);
         a.sorted[(long long)f * a.n_atoms + dst] = s;
         if (a.orig) a.orig[(long long)f * a.n_atoms + dst] = (uint32_t)i;
-        if (a.slot) a.slot[idx] = dst;
+        if (a.slot) a.slot[(long long)f * a.n_atoms + i] = dst;
         if (a.wraps) {
             int *wp = a.wraps + 3 * ((long long)f * a.n_atoms + dst);
             wp[0] = wn[0]; wp[1] = wn[1]; wp[2] = wn[2];
