@@ -80,6 +80,7 @@ SIGNATURES = {
     "amofb_msd_slab_sums": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _dp]),
     "amofb_msd_slab_sums_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _dp]),
     "amofb_msd_slab_sums_begin": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "amofb_msd_slab_sums_begin_strided": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64]),
     "amofb_msd_slab_sums_begin_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "amofb_msd_slab_sums_wait": (C.c_int, [_vp, _dp]),
     "amofb_msd_slab_commit": (C.c_int, [_vp, _dp]),
@@ -401,6 +402,12 @@ class _MsdSession:
         if isinstance(pos, tuple):        # (device pointer, count)
             ctx.check(ctx.lib.amofb_msd_slab_sums_begin_device(ctx.h, int(first), int(pos[1]), pos[0]))
             return int(pos[1])
+        if (isinstance(pos, np.ndarray) and pos.dtype == np.float64 and pos.ndim == 3 and pos.shape[1:] == (self.n, 3)
+                and pos.strides[1:] == (24, 8) and pos.strides[0] > 24 * self.n and pos.strides[0] % 8 == 0):
+            # a column block of wider frames (positions[a:b, lo:hi]): strided copy straight from the caller's array
+            ctx.check(ctx.lib.amofb_msd_slab_sums_begin_strided(ctx.h, int(first), pos.shape[0], pos.ctypes.data, pos.strides[0] // 8))
+            self._keep = pos
+            return pos.shape[0]
         pos = _f64(pos)
         if pos.ndim != 3 or pos.shape[1:] != (self.n, 3):
             raise ValueError("positions slab has shape %r, expected (F, %d, 3)" % (pos.shape, self.n))

@@ -383,7 +383,7 @@ extern "C" int amofb_msd_slab_frames(amofb_ctx *ctx, int *frames) {
 }
 
 // enqueue the copy (host slabs) and the mass sums of one slab; the result is fetched by msd_slab_sums_wait
-static int msd_slab_sums_begin_impl(amofb_ctx *ctx, int first_frame, int count, const double *pos, bool on_device) {
+static int msd_slab_sums_begin_impl(amofb_ctx *ctx, int first_frame, int count, const double *pos, bool on_device, int64_t frame_stride = 0) {
     MsdState *p = nullptr;
     AMOFB_TRY(msd_state(ctx, &p, "amofb_msd_slab_sums"));
     if (p->prepared || p->consumed) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_msd_slab_sums after the positions were transformed");
@@ -402,7 +402,11 @@ static int msd_slab_sums_begin_impl(amofb_ctx *ctx, int first_frame, int count, 
         sl = p->next_stage;
         p->next_stage = (p->next_stage + 1) % 3;
         CUDA_TRY(ctx, cudaEventSynchronize(p->ev_stage[sl]));   // the commit that last read this slot is done
-        CUDA_TRY(ctx, cudaMemcpyAsync(p->d_stage[sl], pos, sizeof(double) * fr * count, cudaMemcpyHostToDevice, ctx->s_copy));
+        if (frame_stride > (int64_t)fr)      // the local atoms are a column block of wider frames: strided copy, no host-side packing
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(p->d_stage[sl], sizeof(double) * fr, pos, sizeof(double) * (size_t)frame_stride, sizeof(double) * fr, (size_t)count,
+                                            cudaMemcpyHostToDevice, ctx->s_copy));
+        else
+            CUDA_TRY(ctx, cudaMemcpyAsync(p->d_stage[sl], pos, sizeof(double) * fr * count, cudaMemcpyHostToDevice, ctx->s_copy));
         cudaEvent_t ev;
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventRecord(ev, ctx->s_copy));
@@ -453,6 +457,10 @@ static int msd_slab_sums_wait_impl(amofb_ctx *ctx, double *sums) {
 
 extern "C" int amofb_msd_slab_sums_begin(amofb_ctx *ctx, int first_frame, int count, const double *pos) {
     return msd_slab_sums_begin_impl(ctx, first_frame, count, pos, false);
+}
+extern "C" int amofb_msd_slab_sums_begin_strided(amofb_ctx *ctx, int first_frame, int count, const double *pos, int64_t frame_stride) {
+    if (ctx && frame_stride < 0) return amofb_fail(ctx, AMOFB_ERR_ARG, "negative frame stride");
+    return msd_slab_sums_begin_impl(ctx, first_frame, count, pos, false, frame_stride);
 }
 extern "C" int amofb_msd_slab_sums_begin_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device) {
     return msd_slab_sums_begin_impl(ctx, first_frame, count, pos_device, true);

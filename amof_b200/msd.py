@@ -83,7 +83,7 @@ def _stream_slabs(session, trajectory, lo, hi, backend, distributed):
     whole = is_array and lo == 0 and hi == trajectory.positions.shape[1]
     ctx = getattr(backend, "ctx", None)
     bufs = None
-    if not whole:       # three staging buffers: a buffer is refilled only after its slab was committed
+    if not is_array:    # three staging buffers: a buffer is refilled only after its slab was committed
         bufs = [ctx.scratch("msdslab%d" % i, (step, n, 3)) if ctx is not None else np.empty((step, n, 3)) for i in range(3)]
     begun = []
 
@@ -94,15 +94,14 @@ def _stream_slabs(session, trajectory, lo, hi, backend, distributed):
 
     for i, a in enumerate(range(0, T, step)):
         b = min(T, a + step)
-        if whole:
-            blk = trajectory.block(a, b)
+        if is_array:
+            blk = trajectory.block(a, b)         # a view; an atom shard is a column block the library copies strided
+            if not whole:
+                blk = blk[:, lo:hi]
         else:
             blk = bufs[i % 3][:b - a]
-            if is_array:
-                blk[...] = trajectory.block(a, b)[:, lo:hi]
-            else:
-                for k in range(a, b):
-                    blk[k - a] = frames._positions_of(trajectory[k])[lo:hi]
+            for k in range(a, b):
+                blk[k - a] = frames._positions_of(trajectory[k])[lo:hi]
         session.slab_sums_begin(a, blk)
         begun.append((a, b))
         if len(begun) == 2:

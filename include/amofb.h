@@ -203,6 +203,9 @@ int amofb_msd_slab_sums_device(amofb_ctx *ctx, int first_frame, int count, const
  * slab's sums into a centre of mass: begin enqueues (at most two slabs may await their commit), wait returns the sums
  * of the oldest slab whose sums were not fetched yet.  slab_sums == begin + wait. */
 int amofb_msd_slab_sums_begin(amofb_ctx *ctx, int first_frame, int count, const double *pos);
+/* strided: frame k of the slab starts at pos + k * frame_stride doubles (frame_stride >= 3 * n_atoms): the local atoms are a
+ * column block of wider frames (an atom-sharded rank reading a whole-frame trajectory), copied without host-side packing */
+int amofb_msd_slab_sums_begin_strided(amofb_ctx *ctx, int first_frame, int count, const double *pos, int64_t frame_stride);
 int amofb_msd_slab_sums_begin_device(amofb_ctx *ctx, int first_frame, int count, const double *pos_device);
 int amofb_msd_slab_sums_wait(amofb_ctx *ctx, double *sums);
 int amofb_msd_slab_commit(amofb_ctx *ctx, const double *com);
