@@ -9,12 +9,17 @@ What runs where
     integer histograms of directed pairs per ordered species pair, accumulated over frames;
   * normalisation (asap3's ``get_rdf``, rdf.py:96,109) -> a few numpy lines below, on the host in fp64.
 
-asap3 is not on disk, so its conventions are pinned here explicitly (same pins as the oracle):
-  U1  bin width is rMax/nBins and bin = int(d / (rMax/nBins)), counted iff < nBins;
-  U3  shell volume of bin i is 4*pi/3 * ((i+1)^3 - i^3) * dr^3;
-  U4  the volume is the mean cell volume over the accumulated frames;
-  a3  every g is count / (n_centre_atoms * n_frames * shell_volume * N_total / V): partials are normalised with
-      the TOTAL number density, which is what makes ``A-X = sum_B A-B`` (rdf.py:111-114) an RDF.
+asap3 is not on disk, so its conventions are pinned here explicitly (same pins as the oracle) -- and, because
+they cannot be checked here, every one of them is a NAMED SWITCH in :data:`CONVENTIONS` with the pin as default:
+  U1  ``bin_rule``      'divide': bin = int(d / (rMax/nBins)) | 'multiply': bin = int(d * (nBins/rMax)); counted iff < nBins.
+                        Decides last-ulp bins; evaluated by the library (amofb_set_option AMOFB_OPT_RDF_BIN_RULE).
+  U3  ``shell_volume``  'exact': 4*pi/3 * ((i+1)^3 - i^3) * dr^3 | 'midpoint': 4*pi * ((i + 1/2) dr)^2 * dr.
+  U4  ``volume``        'mean': mean cell volume over the accumulated frames | 'first': the volume of the first frame.
+  a3  ``partial_norm``  'centre_species': g_ab = count_ab / (N_a * frames * shell * N/V): partials are normalised with the
+                        TOTAL number density, which is what makes ``A-X = sum_B A-B`` (rdf.py:111-114) an RDF that tends to 1
+                        | 'sum_to_global': g_ab = count_ab / (N * frames * shell * N/V), so that sum_ab g_ab is the global RDF.
+The first box with asap3 settles them: tests/golden/make_golden.py writes reference outputs when it can import the
+packages, and tests/test_golden_reference.py compares against them under the defaults.
 """
 import logging
 
@@ -29,6 +34,21 @@ from .trajectory import construct_step
 
 logger = logging.getLogger(__name__)
 
+#: conventions of asap3's RDF that cannot be read off its source here (module docstring); change with set_conventions
+CONVENTIONS = {"bin_rule": "divide", "shell_volume": "exact", "volume": "mean", "partial_norm": "centre_species"}
+_CHOICES = {"bin_rule": ("divide", "multiply"), "shell_volume": ("exact", "midpoint"), "volume": ("mean", "first"),
+            "partial_norm": ("centre_species", "sum_to_global")}
+
+
+def set_conventions(**kwargs):
+    """Change (and return the previous values of) the named conventions, e.g. ``set_conventions(bin_rule='multiply')``."""
+    old = dict(CONVENTIONS)
+    for k, v in kwargs.items():
+        if k not in _CHOICES or v not in _CHOICES[k]:
+            raise ValueError("unknown convention %s=%r (choices: %s)" % (k, v, _CHOICES.get(k)))
+        CONVENTIONS[k] = v
+    return old
+
 
 def _half_cell_rmax(trajectory):
     """min over frames and axes of the cell LENGTHS / 2 (rdf.py:74; lengths, not perpendicular heights).
@@ -38,13 +58,16 @@ def _half_cell_rmax(trajectory):
     return float(np.min(np.sqrt((cells ** 2).sum(axis=2))) / 2)
 
 
-def normalise_counts(counts, n_centres, n_frames, n_atoms, volume_mean, rmax):
-    """counts[bins] of directed pairs -> g(r) (pins U3, U4, a3 above)."""
+def normalise_counts(counts, n_centres, n_frames, n_atoms, volume, rmax):
+    """counts[bins] of directed pairs -> g(r) (pins U3, a3; ``volume`` is the volume pin U4 selected)."""
     bins = len(counts)
     dr = rmax / bins
     i = np.arange(bins, dtype=np.float64)
-    shell = 4.0 * np.pi / 3.0 * (((i + 1.0) * dr) ** 3 - (i * dr) ** 3)
-    norm = shell * (float(n_centres) * float(n_frames)) * (float(n_atoms) / volume_mean)
+    if CONVENTIONS["shell_volume"] == "exact":
+        shell = 4.0 * np.pi / 3.0 * (((i + 1.0) * dr) ** 3 - (i * dr) ** 3)
+    else:
+        shell = 4.0 * np.pi * ((i + 0.5) * dr) ** 2 * dr
+    norm = shell * (float(n_centres) * float(n_frames)) * (float(n_atoms) / volume)
     return np.asarray(counts, dtype=np.float64) / norm
 
 
@@ -63,8 +86,20 @@ def pair_histograms(trajectory, rmax, bins, cn_cutoff=None, distributed=None, ba
     if cn_cutoff is not None:
         from .atom import cutoff_matrix
         cut = cutoff_matrix(cn_cutoff, zs)
-    res = backend.pair_counts(spec, len(zs), frames.iter_chunks(trajectory, lo, hi, backend), rmax=rmax, nbins=bins,
-                              cn_cutoff=cut)
+    ctx = getattr(backend, "ctx", None)
+    rule = 1 if CONVENTIONS["bin_rule"] == "multiply" else 0
+    if ctx is not None:
+        ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, rule)
+    elif rule:
+        raise NotImplementedError("this backend only evaluates the default bin rule")
+    try:
+        res = backend.pair_counts(spec, len(zs), frames.iter_chunks(trajectory, lo, hi, backend), rmax=rmax, nbins=bins,
+                                  cn_cutoff=cut)
+    finally:
+        if ctx is not None and rule:
+            ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, 0)
+    first_cell = np.asarray(frames.gather_cells(trajectory, 0, 1)[0], dtype=np.float64) if T > 0 else np.eye(3)
+    res["volume_first"] = float(abs(np.linalg.det(first_cell)))
     if _dist.active(distributed):
         _, world = _dist.rank_world(distributed)
         if res["hist"] is not None:
@@ -72,8 +107,11 @@ def pair_histograms(trajectory, rmax, bins, cn_cutoff=None, distributed=None, ba
         if res["cn"] is not None:
             counts = [(T * (r + 1)) // world - (T * r) // world for r in range(world)]
             res["cn"] = _dist.allgather_rows(res["cn"], counts, distributed)
-        tot = _dist.allreduce_sum(np.array([res["volume_sum"], float(res["n_frames"])]), distributed)
-        res["volume_sum"], res["n_frames"] = float(tot[0]), int(round(tot[1]))
+        # the float volume sums are gathered and added in rank order, so g(r) does not depend on the reduction tree
+        rank, _ = _dist.rank_world(distributed)
+        per_rank = _dist.allgather_rows(np.array([[res["volume_sum"], float(res["n_frames"])]]), [1] * world, distributed)
+        res["volume_sum"] = float(np.sum(per_rank[:, 0]))        # np.sum over <= 8 addends: sequential
+        res["n_frames"] = int(round(float(np.sum(per_rank[:, 1]))))
     return zs, spec, res
 
 
@@ -134,7 +172,7 @@ class Rdf(object):
         """counts -> the reference's DataFrame (rdf.py:95-114)."""
         hist, n_frames = res["hist"], res["n_frames"]
         n_atoms = len(spec)
-        volume_mean = res["volume_sum"] / n_frames
+        volume_mean = res["volume_sum"] / n_frames if CONVENTIONS["volume"] == "mean" else res["volume_first"]
         n_of = np.bincount(spec, minlength=len(zs))
         idx = {z: k for k, z in enumerate(zs)}
 
@@ -143,7 +181,8 @@ class Rdf(object):
         partial = {}
         for x in atomic_numbers_unique:
             for y in atomic_numbers_unique:
-                g = normalise_counts(hist[idx[int(x)], idx[int(y)]], n_of[idx[int(x)]], n_frames, n_atoms, volume_mean, rmax)
+                n_centres = n_of[idx[int(x)]] if CONVENTIONS["partial_norm"] == "centre_species" else n_atoms
+                g = normalise_counts(hist[idx[int(x)], idx[int(y)]], n_centres, n_frames, n_atoms, volume_mean, rmax)
                 partial[(x, y)] = g
                 columns[chemical_symbols[x] + "-" + chemical_symbols[y]] = g
         for x in atomic_numbers_unique:

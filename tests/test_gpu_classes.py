@@ -116,3 +116,26 @@ def test_c4_bad_counts_against_oracle(backend):
     red = synth.reduced_network("c4", 1)
     zb = amof_b200.bad.Bad.from_trajectory(red, {"Zn-Fr": 4.0}, dtheta=0.5)         # Zn-Im-Zn on the reduced network (Q6 path)
     assert "Zn-Fr-Zn" in zb.data.columns and "X-X-X" in zb.data.columns
+
+
+def test_asap_shim_runs_the_reference_loop(backend):
+    """The reference's own RDF loop (amof/rdf.py:87-114, restated in tests/ref_loops.py) on
+    amof_b200.asap_compat.RadialDistributionFunction: the unmodified amof.rdf would count on the GPU through this class."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from amof_b200 import asap_compat, synth
+    from amof_b200.elements import chemical_symbols
+    from ref_loops import compute_rdf_with
+    traj = synth.make_trajectory("c2", 5)
+    frames_ = [traj[k] for k in range(len(traj))]                      # a list of Atoms, as aMOF holds a trajectory
+    got = compute_rdf_with(asap_compat.RadialDistributionFunction, chemical_symbols, frames_, 0.01, 10.0)
+    want = amof_b200.rdf.Rdf.from_trajectory(traj, dr=0.01, rmax=10.0)
+    assert list(got.columns) == list(want.data.columns)
+    for c in got.columns:
+        np.testing.assert_allclose(got[c].to_numpy(), want.data[c].to_numpy(), rtol=1e-13, atol=0, err_msg=c)
+    obj = asap_compat.RadialDistributionFunction(frames_[0], 10.0, 999)
+    for a in frames_:
+        obj.atoms = a
+        obj.update()
+    hist, zs = obj.get_counts()
+    assert np.array_equal(hist, want.counts) and zs == want.species

@@ -181,3 +181,31 @@ def test_repeated_analyses_reuse_pooled_buffers(backend):
         pos, cell, spec = random_box(n, n, S, True, 14.0)
         res = backend.pair_counts(spec, S, [(pos[None], cell[None])], rmax=6.0, nbins=nb)
         assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell, spec, S, 6.0, nb))
+
+
+def test_bin_rule_option(backend):
+    """AMOFB_OPT_RDF_BIN_RULE (pin U1 as a switch): bin = int(d * (nBins/rMax)) instead of int(d / (rMax/nBins)); on a lattice
+    many distances sit exactly on bin edges, where the two rules can part -- the GPU must follow the oracle under both."""
+    from amof_b200 import _lib
+    cell = np.eye(3) * 8.0
+    g = np.arange(4) * 2.0
+    lattice = np.array([[x, y, z] for x in g for y in g for z in g])
+    rng = np.random.default_rng(8)
+    cases = [(lattice, np.zeros(len(lattice), dtype=np.uint8), 1, 3.9, 39), (lattice, (np.arange(len(lattice)) % 2).astype(np.uint8), 2, 7.3, 999)]
+    pos, cell2, spec = random_box(5, 900, 3, True, 16.0)
+    try:
+        for rule in (1, 0):
+            orc.set_conventions(rule, 0)
+            backend.ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, rule)
+            for p, sp, S, rmax, nb in cases:
+                res = backend.pair_counts(sp, S, [(p[None], cell[None])], rmax=rmax, nbins=nb)
+                assert np.array_equal(res["hist"], orc.rdf_hist(p, cell, sp, S, rmax, nb)), (rule, rmax)
+            res = backend.pair_counts(spec, 3, [(pos[None], cell2[None])], rmax=7.0, nbins=700)
+            assert np.array_equal(res["hist"], orc.rdf_hist(pos, cell2, spec, 3, 7.0, 700))
+        with pytest.raises(ValueError):
+            backend.ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, 7)
+        with pytest.raises(ValueError):
+            backend.ctx.set_option(99, 0)
+    finally:
+        orc.set_conventions(0, 0)
+        backend.ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, 0)
