@@ -12,7 +12,7 @@ Same module and class names as the reference package ``amof``::
 All counting runs in hand-written CUDA kernels behind the C ABI of include/amofb.h (libamofb.so, loaded with
 ctypes on first use).  There is no CPU fallback: computing without the library or without a CUDA device raises.
 """
-from . import atom, bad, cn, elements, files, msd, rdf, synth, trajectory  # noqa: F401
+from . import asap_compat, atom, bad, cn, elements, files, msd, rdf, sq, synth, trajectory  # noqa: F401
 from .atoms import Atoms, read_extxyz  # noqa: F401
 from .frames import ArrayTrajectory  # noqa: F401
 

@@ -317,3 +317,37 @@ def test_get_neighborlist_host_logic(zif4):
     np.testing.assert_allclose(np.linalg.norm(pos[nbr] - pos[owner] + shifts @ cell, axis=1), dist, rtol=0, atol=1e-12)
     lim = np.where((numbers[owner] == 30) | (numbers[nbr] == 30), 2.5, 1.728)
     assert np.all(dist < lim)
+
+
+# ------------------------------------------------------------------------------------------------ structure factor
+def test_structure_factor_ideal_gas_and_fcc():
+    """S(q) from the partial histograms (amof_b200.sq): an ideal gas has S = 1 within the counting noise; an fcc crystal with
+    a little thermal noise has Bragg peaks at 2 pi / a * sqrt(3), sqrt(8), sqrt(11) ((200) is a shoulder of (111) at the
+    resolution rmax = 12 A gives)."""
+    from amof_b200 import sq
+    rng = np.random.default_rng(4)
+    cell = np.eye(3) * 24.0
+    gas = [Atoms(numbers=[18] * 3000, positions=rng.uniform(0, 24, (3000, 3)), cell=cell) for _ in range(3)]
+    s = sq.StructureFactor.from_trajectory(gas, dr=0.05, rmax=11.0, q=np.arange(1.0, 10.0, 0.1))
+    assert list(s.data.columns) == ["q", "X-X", "Ar-Ar"]
+    assert np.all(np.abs(s.data["X-X"].to_numpy() - 1.0) < 0.15)
+    np.testing.assert_allclose(s.data["X-X"].to_numpy(), s.data["Ar-Ar"].to_numpy(), rtol=1e-12)
+    a = 4.0
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) * a
+    cells_ = np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)]) * a
+    pos = (cells_[:, None, :] + base[None, :, :]).reshape(-1, 3)
+    numbers = np.where(np.arange(len(pos)) % 2 == 0, 29, 47)            # two species on one lattice: partials share the peaks
+    fcc = [Atoms(numbers=numbers, positions=pos + rng.normal(scale=0.05, size=pos.shape), cell=np.eye(3) * 6 * a) for _ in range(2)]
+    q = np.arange(1.5, 6.0, 0.01)
+    s = sq.StructureFactor.from_trajectory(fcc, dr=0.02, q=q)
+    assert list(s.data.columns) == ["q", "X-X", "Cu-Cu", "Cu-Ag", "Ag-Ag"]
+    tot = s.data["X-X"].to_numpy()
+    peaks = [q[i] for i in range(1, len(q) - 1) if tot[i] > tot[i - 1] and tot[i] > tot[i + 1] and tot[i] > 1.5]
+    want = 2 * np.pi / a * np.sqrt([3, 8, 11])
+    assert len(peaks) >= 3
+    for w in want:
+        assert min(abs(p - w) for p in peaks) < 0.08, (w, peaks)
+    c = s.concentrations
+    mix = sum(c[x] * c[y] * s.data["%s-%s" % (amof_b200.elements.chemical_symbols[min(x, y)], amof_b200.elements.chemical_symbols[max(x, y)])].to_numpy()
+              for x in c for y in c)
+    np.testing.assert_allclose(mix, tot, rtol=1e-10, atol=1e-10)         # S = sum_ab c_a c_b S_ab

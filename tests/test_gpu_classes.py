@@ -1,5 +1,6 @@
 """The drop-in classes on the GPU against the restated reference driver code (oracle/ref_classes.py): same columns,
 same values (normalised outputs within 1e-12 relative), plus size-independent properties on a larger workload."""
+import os
 import numpy as np
 import pytest
 
