@@ -137,8 +137,8 @@ def _numbers_of(atoms):
 
 def check_same_atoms(trajectory, numbers, lo, hi):
     """The C ABI takes one species vector per analysis; aMOF trajectories keep atom order fixed."""
-    if isinstance(trajectory, ArrayTrajectory):
-        return
+    if isinstance(trajectory, ArrayTrajectory) or hasattr(trajectory, "stream_chunks"):
+        return                                   # one species vector by construction (a stream checks the symbols as it parses)
     for k in range(lo, hi):
         z = _numbers_of(trajectory[k])
         if z is numbers:
@@ -151,7 +151,7 @@ def check_same_atoms(trajectory, numbers, lo, hi):
 def gather_cells(trajectory, lo=0, hi=None):
     """cells[hi-lo][3][3] of the frames [lo, hi)"""
     hi = len(trajectory) if hi is None else hi
-    if isinstance(trajectory, ArrayTrajectory):
+    if isinstance(trajectory, ArrayTrajectory) or hasattr(trajectory, "stream_chunks"):
         return trajectory.cells[lo:hi]
     out = np.empty((max(hi - lo, 0), 3, 3))
     for k in range(lo, hi):
@@ -166,6 +166,9 @@ def iter_chunks(trajectory, lo, hi, backend, target_bytes=192 << 20):
     obtained from the backend's context (plain numpy buffers when the backend has none); the per-frame work in the
     interpreter is two attribute reads, the copies of a chunk are one ``np.concatenate`` into the buffer."""
     if hi <= lo:
+        return
+    if hasattr(trajectory, "stream_chunks"):     # a lazily read file (amof_b200.stream.XyzStream): parsed ahead by its own threads
+        yield from trajectory.stream_chunks(lo, hi, backend)
         return
     ctx = getattr(backend, "ctx", None)
     is_array = isinstance(trajectory, ArrayTrajectory)

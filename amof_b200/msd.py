@@ -33,7 +33,7 @@ def _atom_range(n_atoms, distributed):
 
 
 def _cells_of(trajectory):
-    if isinstance(trajectory, frames.ArrayTrajectory):
+    if isinstance(trajectory, frames.ArrayTrajectory) or hasattr(trajectory, "stream_chunks"):
         return trajectory.cells
     return np.array([np.asarray(a.get_cell(), dtype=np.float64).reshape(3, 3) for a in trajectory])
 

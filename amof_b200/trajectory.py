@@ -1,8 +1,10 @@
 """
 Trajectory-level helpers with the reference's names (/root/reference/amof/trajectory.py:230-303).
 
-File readers (``read_cp2k_traj`` ...) are ase.io's job and stay with the reference;
-``get_delta_pos`` lives on the GPU inside the MSD analysis (amofb_msd_* in include/amofb.h).
+``read_lammps_traj`` / ``read_cp2k_traj`` keep the reference's names and arguments (trajectory.py:193-228) but return a
+lazily read :class:`amof_b200.stream.XyzStream` instead of a list of Atoms: still a valid aMOF trajectory, and the analyses
+parse it in chunks while the GPU works.  ``get_delta_pos`` lives on the GPU inside the MSD
+analysis (amofb_msd_* in include/amofb.h).
 """
 import logging
 
@@ -60,6 +62,19 @@ def read_extxyz_trajectory(path):
     numbers = np.array([atomic_numbers[str(s)] for s in symbols], dtype=np.int64)
     positions = np.ascontiguousarray(body[["x", "y", "z"]].to_numpy(dtype=np.float64).reshape(T, n, 3))
     return ArrayTrajectory(numbers, positions, np.array(cells, dtype=np.float64).reshape(T, 3, 3))
+
+
+def read_lammps_traj(path_to_xyz, index=None, cell=None, unzip_xyz=False):
+    """xyz trajectory (optionally gzipped) with an optional cell -- one 3x3 cell or one per frame (trajectory.py:193-206).
+    Without ``cell`` the file must carry extended-XYZ ``Lattice=`` headers."""
+    from .stream import XyzStream
+    return XyzStream(path_to_xyz, cell=cell, index=index, unzip=unzip_xyz)
+
+
+def read_cp2k_traj(path_to_xyz, path_to_cell, index=None, unzip_xyz=False):
+    """CP2K xyz trajectory + ``.cell`` file (trajectory.py:208-228); ``index`` is a slice."""
+    from .stream import XyzStream, read_cp2k_cell
+    return XyzStream(path_to_xyz, cell=read_cp2k_cell(path_to_cell, index), index=index, unzip=unzip_xyz)
 
 
 def apply_to_traj(trajectory, function, how):

@@ -351,3 +351,73 @@ def test_structure_factor_ideal_gas_and_fcc():
     mix = sum(c[x] * c[y] * s.data["%s-%s" % (amof_b200.elements.chemical_symbols[min(x, y)], amof_b200.elements.chemical_symbols[max(x, y)])].to_numpy()
               for x in c for y in c)
     np.testing.assert_allclose(mix, tot, rtol=1e-10, atol=1e-10)         # S = sum_ab c_a c_b S_ab
+
+
+# ------------------------------------------------------------------------------------------------ streaming ingest
+def _write_xyz(path, traj, extended=True, gz=False):
+    import gzip
+    sym = traj[0].get_chemical_symbols()
+    lines = []
+    for a in traj:
+        lines.append("%d" % len(a))
+        if extended:
+            lines.append('Lattice="%s" Properties=species:S:1:pos:R:3 pbc="T T T"' % " ".join(repr(float(x)) for x in np.asarray(a.get_cell()).ravel()))
+        else:
+            lines.append(" i = 1, time = 0.5, E = -1.0")
+        for s, p in zip(sym, a.get_positions()):
+            lines.append("%s %r %r %r" % (s, float(p[0]), float(p[1]), float(p[2])))
+    data = ("\n".join(lines) + "\n").encode()
+    with (gzip.open(path, "wb") if gz else open(path, "wb")) as fh:
+        fh.write(data)
+
+
+def test_streaming_readers(tmp_path):
+    """amof_b200.stream.XyzStream behind the reference's reader names: extended XYZ, xyz + cell array, CP2K xyz + .cell file,
+    gzip; lazily indexed frames and streamed chunks are bit-identical to what was written, and the analyses give the same
+    DataFrames from the stream as from the list of Atoms."""
+    from amof_b200 import stream, trajectory as amtraj
+    traj = small_traj(7)
+    want_pos = np.array([t.get_positions() for t in traj])
+    want_cell = np.array([np.asarray(t.get_cell()) for t in traj])
+    p1 = str(tmp_path / "ext.xyz")
+    _write_xyz(p1, traj, extended=True)
+    s1 = amtraj.read_lammps_traj(p1)
+    assert len(s1) == 7 and np.array_equal(s1.numbers, traj[0].get_atomic_numbers())
+    assert np.array_equal(s1.cells, want_cell)
+    assert np.array_equal(s1[3].get_positions(), want_pos[3]) and np.array_equal(s1[-1].get_positions(), want_pos[6])
+    s1._chunk_frames = 2                                      # several chunks, several parser threads
+    got = list(s1.stream_chunks(1, 6, None))
+    assert [len(c[0]) for c in got] == [2, 2, 1]
+    assert np.array_equal(np.concatenate([c[0] for c in got]), want_pos[1:6])
+    assert np.array_equal(np.concatenate([c[1] for c in got]), want_cell[1:6])
+    # CP2K: plain xyz + cell file (Step Time Ax..Cz Volume), gzipped, with a slice
+    p2 = str(tmp_path / "cp2k-pos.xyz.gz")
+    _write_xyz(p2, traj, extended=False, gz=True)
+    pc = str(tmp_path / "cp2k.cell")
+    with open(pc, "w") as fh:
+        fh.write("#   Step   Time [fs]       Ax [Angstrom] ...\n")
+        for k, c in enumerate(want_cell):
+            fh.write("%8d %12.3f " % (k, 0.5 * k) + " ".join(repr(float(x)) for x in c.ravel()) + " %r\n" % float(abs(np.linalg.det(c))))
+    s2 = amtraj.read_cp2k_traj(p2, pc, index=slice(1, 7, 2), unzip_xyz=True)
+    assert len(s2) == 3 and np.array_equal(s2.cells, want_cell[1:7:2])
+    assert np.array_equal(np.concatenate([c[0] for c in s2.stream_chunks(0, 3, None)]), want_pos[1:7:2])
+    # xyz + one constant cell; a cell array shorter than the file trims the trajectory like Trajectory.set_cell(fit_size=True)
+    p3 = str(tmp_path / "plain.xyz")
+    _write_xyz(p3, traj, extended=False)
+    s3 = amtraj.read_lammps_traj(p3, cell=want_cell[0])
+    assert len(s3) == 7 and np.array_equal(s3.cells[5], want_cell[0])
+    s4 = amtraj.read_lammps_traj(p3, cell=want_cell[:5])
+    assert len(s4) == 5
+    with pytest.raises(ValueError):
+        amtraj.read_lammps_traj(p3)                           # no Lattice= and no cell
+    # the analyses take the stream as they take the list
+    a = amof_b200.rdf.Rdf.from_trajectory(s1, dr=0.05, rmax=5.0)
+    b = amof_b200.rdf.Rdf.from_trajectory(traj, dr=0.05, rmax=5.0)
+    assert_frames_equal(a.data, b.data)
+    assert np.array_equal(a.counts, b.counts)
+    assert_frames_equal(amof_b200.cn.CoordinationNumber.from_trajectory(s1, {"Zn-N": 2.5}).data,
+                        amof_b200.cn.CoordinationNumber.from_trajectory(traj, {"Zn-N": 2.5}).data)
+    assert_frames_equal(amof_b200.bad.Bad.from_trajectory(s1, {"Zn-N": 2.5}, dtheta=1.0).data,
+                        amof_b200.bad.Bad.from_trajectory(traj, {"Zn-N": 2.5}, dtheta=1.0).data)
+    assert_frames_equal(amof_b200.msd.WindowMsd.from_trajectory(s1, delta_time=1, timestep=1, mutate=False).data,
+                        amof_b200.msd.WindowMsd.from_trajectory(traj, delta_time=1, timestep=1, mutate=False).data)

@@ -140,3 +140,25 @@ def test_asap_shim_runs_the_reference_loop(backend):
         obj.update()
     hist, zs = obj.get_counts()
     assert np.array_equal(hist, want.counts) and zs == want.species
+
+
+def test_streamed_file_matches_in_memory(backend, tmp_path):
+    """An extended-XYZ file analysed through amof_b200.stream.XyzStream (parser threads filling page-locked buffers ahead of
+    the GPU) gives the integers of the same frames held in memory."""
+    from amof_b200 import stream, synth
+    from amof_b200.elements import chemical_symbols
+    traj = synth.make_trajectory("c2", 9)
+    sym = [chemical_symbols[z] for z in traj.numbers]
+    path = str(tmp_path / "c2.xyz")
+    with open(path, "w") as fh:
+        for k in range(len(traj)):
+            fh.write('%d\nLattice="%s" Properties=species:S:1:pos:R:3\n' % (len(sym), " ".join(repr(float(x)) for x in traj.cells[k].ravel())))
+            fh.write("\n".join("%s %r %r %r" % (s, float(p[0]), float(p[1]), float(p[2])) for s, p in zip(sym, traj.positions[k])) + "\n")
+    s = stream.XyzStream(path, chunk_bytes=1 << 20, threads=3)          # two frames per chunk
+    sets = {'Zn-N': 2.5, 'C-N': 1.728}
+    r1, c1 = amof_b200.rdf.rdf_and_cn(s, sets, dr=0.01, rmax=10.0)
+    r2, c2 = amof_b200.rdf.rdf_and_cn(traj, sets, dr=0.01, rmax=10.0)
+    assert np.array_equal(r1.counts, r2.counts) and np.array_equal(c1.counts, c2.counts)
+    b1 = amof_b200.bad.Bad.from_trajectory(s, {'Zn-N': 2.5})
+    b2 = amof_b200.bad.Bad.from_trajectory(traj, {'Zn-N': 2.5})
+    assert np.array_equal(b1.counts["N-Zn-N"], b2.counts["N-Zn-N"])
