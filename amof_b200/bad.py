@@ -186,12 +186,56 @@ class BadByCn(CoreBad):
         return xr.Dataset({'bad': xa})
 
     def write_to_file(self, filename):
-        if self.data is None:
-            raise ImportError("BadByCn.write_to_file needs xarray (netCDF output, bad.py:303-305)")
+        """netCDF like the reference's ``xr.Dataset.to_netcdf`` (bad.py:303-305): variable ``bad`` over (atom_triple, cn, theta)
+        with its three coordinates.  Without xarray the same classic-format file is written through scipy.io.netcdf_file (what
+        xarray's own scipy engine writes: fixed-width character array for the string coordinate, NaN where a triple has no
+        centre of that coordination number)."""
         filename = _path.append_suffix(filename, 'bad')
-        self.data.to_netcdf(filename)
+        if self.data is not None:
+            self.data.to_netcdf(filename)
+            return
+        from scipy.io import netcdf_file
+        names = list(self.by_cn)
+        cns = sorted({cn for d in self.by_cn.values() for cn in d})
+        width = max([len(n) for n in names] + [1])
+        with netcdf_file(filename, 'w') as nc:
+            nc.createDimension('atom_triple', len(names))
+            nc.createDimension('cn', len(cns))
+            nc.createDimension('theta', len(self.theta))
+            nc.createDimension('string%d' % width, width)
+            v = nc.createVariable('atom_triple', 'c', ('atom_triple', 'string%d' % width))
+            for i, n in enumerate(names):
+                v[i] = np.array(list(n.ljust(width, '\0')), dtype='S1')
+            v = nc.createVariable('cn', 'i', ('cn',))
+            v[:] = np.array(cns, dtype=np.int32)
+            v = nc.createVariable('theta', 'd', ('theta',))
+            v[:] = self.theta
+            v = nc.createVariable('bad', 'd', ('atom_triple', 'cn', 'theta'))
+            v._FillValue = np.nan
+            block = np.full((len(names), len(cns), len(self.theta)), np.nan)
+            for i, n in enumerate(names):
+                for cn, dens in self.by_cn[n].items():
+                    block[i, cns.index(cn)] = dens
+            v[:] = block
 
     def read_bad_file(self, filename):
-        import xarray as xr
         filename = _path.append_suffix(filename, 'bad')
-        self.data = xr.open_dataset(filename)
+        try:
+            import xarray as xr
+        except ImportError:
+            xr = None
+        if xr is not None:
+            self.data = xr.open_dataset(filename)
+            names = [str(n) for n in self.data['atom_triple'].values]
+            cns = [int(c) for c in self.data['cn'].values]
+            self.theta = np.asarray(self.data['theta'].values, dtype=np.float64)
+            block = np.asarray(self.data['bad'].values, dtype=np.float64)
+        else:
+            from scipy.io import netcdf_file
+            with netcdf_file(filename, 'r', mmap=False) as nc:
+                raw = nc.variables['atom_triple'][:]
+                names = [b"".join(row).decode().rstrip("\0").rstrip() for row in raw]
+                cns = [int(c) for c in nc.variables['cn'][:]]
+                self.theta = np.array(nc.variables['theta'][:], dtype=np.float64)
+                block = np.array(nc.variables['bad'][:], dtype=np.float64)
+        self.by_cn = {n: {cn: block[i, j] for j, cn in enumerate(cns) if not np.all(np.isnan(block[i, j]))} for i, n in enumerate(names)}

@@ -161,6 +161,28 @@ def test_bad_by_cn(zif4):
     np.testing.assert_allclose(summed, whole.data["N-Zn-N"], rtol=1e-12, atol=1e-300)
 
 
+def test_bad_by_cn_netcdf_roundtrip(tmp_path):
+    """BadByCn.write_to_file / from_file (bad.py:303-309): a classic netCDF file with variable 'bad' over (atom_triple, cn,
+    theta); written through xarray when it is there, through scipy.io.netcdf_file otherwise -- the file is the same."""
+    from scipy.io import netcdf_file
+    traj = small_traj(3, sigma=0.25)                        # enough disorder for several coordination numbers
+    b = amof_b200.bad.BadByCn.from_trajectory(traj, {"Zn-N": 2.5, "C-N": 1.728}, dtheta=1.0, normalization='partial')
+    assert len(b.by_cn) >= 2 and any(len(d) > 1 for d in b.by_cn.values())
+    b.write_to_file(tmp_path / "bycn")
+    assert (tmp_path / "bycn.bad").exists()
+    with netcdf_file(str(tmp_path / "bycn.bad"), 'r', mmap=False) as nc:
+        assert set(nc.variables) == {"atom_triple", "cn", "theta", "bad"}
+        assert nc.variables["bad"].dimensions == ("atom_triple", "cn", "theta")
+        assert nc.variables["bad"].shape[2] == len(b.theta)
+    back = amof_b200.bad.BadByCn.from_file(tmp_path / "bycn")
+    assert sorted(back.by_cn) == sorted(b.by_cn)
+    np.testing.assert_array_equal(back.theta, b.theta)
+    for name, d in b.by_cn.items():
+        assert sorted(back.by_cn[name]) == sorted(d)
+        for cn, dens in d.items():
+            np.testing.assert_array_equal(back.by_cn[name][cn], dens)
+
+
 def test_bad_file_roundtrip(tmp_path, zif4):
     b = amof_b200.bad.Bad.from_trajectory([zif4], {"Zn-N": 2.5}, dtheta=1.0)
     b.write_to_file(tmp_path / "a")
