@@ -88,6 +88,8 @@ SIGNATURES = {
     "amofb_msd_direct": (C.c_int, [_vp, _dp]),
     "amofb_msd_get_positions": (C.c_int, [_vp, _dp]),
     "amofb_msd_end": (C.c_int, [_vp]),
+    "amofb_xyz_index": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _i64p, C.c_int64, _i64p, _i64p]),
+    "amofb_xyz_parse": (C.c_int, [C.c_char_p, _i64p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
 }
 
 _lib = None
@@ -118,6 +120,34 @@ def load_library():
 
 def _ptr(a, typ):
     return a.ctypes.data_as(typ)
+
+
+def xyz_index(text, lines_before, period, base):
+    """amofb_xyz_index on one block of a file: (file offsets of the frames starting after a newline of this block, newlines seen)"""
+    lib = load_library()
+    cap = len(text) // max(1, 2 * int(period)) + 2      # a line is at least 2 bytes
+    starts = np.empty(cap, dtype=np.int64)
+    n, lines = C.c_int64(0), C.c_int64(0)
+    rc = lib.amofb_xyz_index(text, len(text), int(lines_before), int(period), int(base), _ptr(starts, _i64p), cap, C.byref(n), C.byref(lines))
+    if rc != 0:
+        raise ValueError("amofb_xyz_index failed (%d)" % rc)
+    return starts[:n.value], lines.value
+
+
+def xyz_parse(text, frame_off, n_atoms, pos_col, symbols, symbols_known, out, threads=0):
+    """amofb_xyz_parse (host code of the library: needs no CUDA device).  ``text`` bytes, ``frame_off`` int64[F + 1] offsets into it,
+    ``symbols`` a writable bytearray of 8 * n_atoms, ``out`` float64[>= F][n_atoms][3] C-contiguous."""
+    lib = load_library()
+    frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
+    F = len(frame_off) - 1
+    assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= F * n_atoms * 3
+    bad = C.c_int(-1)
+    sym = (C.c_char * len(symbols)).from_buffer(symbols)
+    rc = lib.amofb_xyz_parse(text, _ptr(frame_off, _i64p), F, int(n_atoms), int(pos_col), sym, int(bool(symbols_known)),
+                             _ptr(out, _dp), int(threads), C.byref(bad))
+    if rc != 0:
+        raise ValueError("XYZ text: frame %d of the block is truncated or malformed, or its atom order differs from the first frame's"
+                         % bad.value)
 
 
 class Context:

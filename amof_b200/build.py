@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libamofb.so")
-SOURCES = ["amofb.cu"]
-DEPS = ["amofb.cu", "common.cuh", "prep.cuh", "pair.cuh", "pair_tiled.cuh", "neigh.cuh", "neigh_host.inl", "bad.cuh", "msd.cuh", "bad_host.inl", "msd_host.inl",
+SOURCES = ["amofb.cu", "xyz_parse.cpp"]
+DEPS = ["amofb.cu", "xyz_parse.cpp", "common.cuh", "prep.cuh", "pair.cuh", "pair_tiled.cuh", "neigh.cuh", "neigh_host.inl", "bad.cuh", "msd.cuh", "bad_host.inl", "msd_host.inl",
         os.path.join("..", "..", "include", "amofb.h")]
 
 

@@ -8,14 +8,13 @@ trajectory.py:193-228).  End to end that list is the bottleneck, 
   * a valid aMOF trajectory -- ``len()``, indexing (a frame is parsed when asked for), iteration -- whose cells are known
     up front (extended-XYZ ``Lattice=`` headers, a constant cell, a cell array, or the CP2K cell file);
   * and a chunk source for the analyses: :func:`amof_b200.frames.iter_chunks` asks it for ``(positions, cells)`` blocks, which
-    a few parser threads (pandas' C tokenizer releases the GIL) fill into a ring of page-locked buffers ahead of the consumer,
+    the library's native parser (``amofb_xyz_parse``, all host cores) fills into a ring of page-locked buffers ahead of the consumer,
     so chunk k+1.. are being parsed while chunk k is copied and counted.
 
 One pass over the file finds where every frame starts (newline counting on raw bytes, vectorised); gzipped files are
 inflated to a temporary file first, as ``Trajectory.from_traj(unzip=True)`` does.
 """
 import gzip
-import io
 import logging
 import os
 import shutil
@@ -32,6 +31,7 @@ logger = logging.getLogger(__name__)
 
 def _frame_offsets(path, period):
     """byte offset of the first line of every frame (a frame = ``period`` lines), and the file size"""
+    from . import _lib
     size = os.path.getsize(path)
     starts = [np.zeros(1, dtype=np.int64)]
     lines_before = 0
@@ -41,13 +41,9 @@ def _frame_offsets(path, period):
             buf = fh.read(64 << 20)
             if not buf:
                 break
-            nl = np.flatnonzero(np.frombuffer(buf, dtype=np.uint8) == 10)
-            # newline i of this block ends line (lines_before + i); the line after it starts a frame when its number is a
-            # multiple of the period
-            ends = lines_before + 1 + np.arange(len(nl), dtype=np.int64)
-            hit = ends % period == 0
-            starts.append(base + nl[hit].astype(np.int64) + 1)
-            lines_before += len(nl)
+            found, lines = _lib.xyz_index(buf, lines_before, period, base)
+            starts.append(found)
+            lines_before += lines
             base += len(buf)
     offs = np.concatenate(starts)
     offs = offs[offs < size]                       # a trailing newline does not start a frame
@@ -65,8 +61,9 @@ class XyzStream(object):
         unzip: inflate a gzipped file to a temporary file first (implied by a ``.gz`` suffix)
     """
 
-    def __init__(self, path, cell=None, index=None, unzip=False, chunk_bytes=48 << 20, threads=None):
+    def __init__(self, path, cell=None, index=None, unzip=False, chunk_bytes=32 << 20, threads=None):
         self._tmp = None
+        self._symbytes = None
         if unzip or str(path).endswith(".gz"):
             logger.info("Unzip trajectory file")
             self._tmp = tempfile.NamedTemporaryFile(suffix=".xyz")
@@ -130,50 +127,42 @@ class XyzStream(object):
         self._first_positions = first[0][0] if self.n_frames else None
         frame_bytes = max(1, int((self._offs_all[-1]) // max(n_file, 1)))
         self._chunk_frames = max(1, int(chunk_bytes // frame_bytes))
-        self._threads = threads or max(1, min(8, (os.cpu_count() or 2) // 2))
+        self._threads = threads or max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)))
 
     # ---- parsing ---------------------------------------------------------------------------------------
-    def _parse_frames(self, frame_ids, out=None):
-        """positions [len(frame_ids)][N][3] of the given file frames (+ the symbols of the first one)"""
-        import pandas as pd
-        bodies = []
+    def _parse_frames(self, frame_ids, out=None, threads=1):
+        """positions [len(frame_ids)][N][3] of the given file frames (+ the symbols of the first one), through the library's
+        native parser (amofb_xyz_parse: correctly rounded decimal -> binary64, like float(); ctypes releases the GIL)"""
+        from . import _lib
+        ids = np.asarray(frame_ids, dtype=np.int64)
+        n = self.n_atoms
+        if out is None:
+            out = np.empty((len(ids), n, 3))
+        known = getattr(self, "_symbytes", None) is not None
+        symbytes = self._symbytes if known else bytearray(8 * n)
         with open(self.path, "rb") as fh:
-            runs = []
-            ids = np.asarray(frame_ids)
             i = 0
-            while i < len(ids):                   # consecutive file frames are one read
+            while i < len(ids):                   # consecutive file frames are one read and one call
                 j = i
                 while j + 1 < len(ids) and ids[j + 1] == ids[j] + 1:
                     j += 1
-                runs.append((ids[i], ids[j]))
-                i = j + 1
-            for a, b in runs:
-                fh.seek(int(self._offs_all[a]))
-                buf = fh.read(int(self._offs_all[b + 1] - self._offs_all[a]))
+                a, b = int(ids[i]), int(ids[j])
                 base = int(self._offs_all[a])
-                for k in range(a, b + 1):
-                    lo = int(self._offs_all[k]) - base
-                    hi = int(self._offs_all[k + 1]) - base
-                    p = buf.find(b"\n", lo) + 1
-                    p = buf.find(b"\n", p) + 1                      # skip the count and the comment line
-                    bodies.append(buf[p:hi])
-        pc = self._pos_col
-        body = pd.read_csv(io.BytesIO(b"".join(bodies)), sep=r"\s+", header=None, usecols=[0, pc, pc + 1, pc + 2], engine="c",
-                           names=["s", "x", "y", "z"], float_precision="round_trip")      # bit-exact decimal -> binary64, like float()
-        n = self.n_atoms
-        if len(body) != len(frame_ids) * n:
-            raise ValueError("truncated XYZ file: %d atom lines for %d frames of %d atoms" % (len(body), len(frame_ids), n))
-        sym = body["s"].to_numpy()
-        symbols = [str(s) for s in sym[:n]]
-        if getattr(self, "_symbols", None):
-            want = np.array(self._symbols, dtype=object)
-            if not (sym.reshape(len(frame_ids), n) == want[None, :]).all():
-                raise ValueError("atom order changes between frames")
-        pos = body[["x", "y", "z"]].to_numpy(dtype=np.float64).reshape(len(frame_ids), n, 3)
-        if out is not None:
-            out[:len(frame_ids)] = pos
-            pos = out[:len(frame_ids)]
-        return pos, symbols
+                fh.seek(base)
+                buf = fh.read(int(self._offs_all[b + 1]) - base)
+                if len(buf) != int(self._offs_all[b + 1]) - base:
+                    raise ValueError("truncated XYZ file")
+                try:
+                    _lib.xyz_parse(buf, self._offs_all[a:b + 2] - base, n, self._pos_col, symbytes, known, out[i:j + 1],
+                                   threads=threads)
+                except ValueError as err:
+                    raise ValueError("%s: %s (block starting at file frame %d)" % (self.path, err, a))
+                known = True
+                i = j + 1
+        if getattr(self, "_symbytes", None) is None:
+            self._symbytes = symbytes
+        symbols = [bytes(symbytes[8 * k:8 * k + 8]).rstrip(b"\0").decode() for k in range(n)] if len(ids) else []
+        return out[:len(ids)], symbols
 
     # ---- the aMOF trajectory surface -------------------------------------------------------------------
     def __len__(self):
@@ -202,23 +191,25 @@ class XyzStream(object):
             return
         ctx = getattr(backend, "ctx", None)
         F = min(self._chunk_frames, hi - lo)
-        nslot = self._threads + 2
+        workers = 2 if self._threads > 1 else 1            # one block being parsed while the next is being read
+        native = max(1, self._threads // workers)
+        nslot = workers + 2
         if ctx is not None:
             bufs = [ctx.scratch("xyzstream%d" % i, (F, self.n_atoms, 3)) for i in range(nslot)]
         else:
             bufs = [np.empty((F, self.n_atoms, 3)) for _ in range(nslot)]
         spans = [(a, min(hi, a + F)) for a in range(lo, hi, F)]
-        with ThreadPoolExecutor(max_workers=self._threads) as pool:
+        with ThreadPoolExecutor(max_workers=workers) as pool:
             pending = []
             nxt = 0
 
             def submit():
                 nonlocal nxt
                 a, b = spans[nxt]
-                pending.append((a, b, pool.submit(self._parse_frames, self._sel[a:b], bufs[nxt % nslot])))
+                pending.append((a, b, pool.submit(self._parse_frames, self._sel[a:b], bufs[nxt % nslot], native)))
                 nxt += 1
 
-            while nxt < len(spans) and len(pending) < self._threads:
+            while nxt < len(spans) and len(pending) < workers:
                 submit()
             done = 0
             while pending:

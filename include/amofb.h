@@ -214,6 +214,27 @@ int amofb_msd_direct(amofb_ctx *ctx, double *sums);
 int amofb_msd_get_positions(amofb_ctx *ctx, double *pos);
 int amofb_msd_end(amofb_ctx *ctx);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Trajectory text ingest (host code, no device work): the step in front of every analysis, replacing the per-frame
+ * Python parsing of ase.io.read(filename, index, 'xyz') (/root/reference/amof/trajectory.py:48-60,193-228).
+ *
+ * xyz_parse: n_frames XYZ / extended-XYZ frames out of a text buffer; frame k occupies text[frame_off[k] .. frame_off[k+1])
+ *            and is a count line, a comment line and n_atoms atom lines "Symbol ... x y z ...", x being whitespace-separated
+ *            column pos_col (1 in plain XYZ).  positions double[n_frames][n_atoms][3] receives the coordinates, every decimal
+ *            string converted with correct rounding (the value Python's float() gives).  symbols is char[n_atoms][8],
+ *            NUL-padded: filled from the first frame when symbols_known == 0, otherwise every frame is checked against it.
+ *            Frames are spread over `threads` host threads (<= 0: one per core, at most 16).
+ *            AMOFB_ERR_ARG: malformed or truncated frame, or an atom order that changes; *bad_frame (may be NULL) says which.
+ * xyz_index: where frames start.  Scans a block of the file (text[0 .. len), whose first byte is byte `base` of the file and
+ *            which `lines_before` complete lines precede) and writes the file offset of every line whose number is a multiple of
+ *            `period` (= n_atoms + 2) into starts[capacity]; *n_starts = how many there are (AMOFB_ERR_MEMORY if more than
+ *            capacity: nothing beyond capacity is written), *n_lines = newlines seen in the block.
+ */
+int amofb_xyz_index(const char *text, int64_t len, int64_t lines_before, int64_t period, int64_t base, int64_t *starts,
+                    int64_t capacity, int64_t *n_starts, int64_t *n_lines);
+int amofb_xyz_parse(const char *text, const int64_t *frame_off, int n_frames, int n_atoms, int pos_col, char *symbols,
+                    int symbols_known, double *positions, int threads, int *bad_frame);
+
 #ifdef __cplusplus
 }
 #endif

@@ -443,3 +443,47 @@ def test_streaming_readers(tmp_path):
                         amof_b200.bad.Bad.from_trajectory(traj, {"Zn-N": 2.5}, dtheta=1.0).data)
     assert_frames_equal(amof_b200.msd.WindowMsd.from_trajectory(s1, delta_time=1, timestep=1, mutate=False).data,
                         amof_b200.msd.WindowMsd.from_trajectory(traj, delta_time=1, timestep=1, mutate=False).data)
+
+
+def test_native_xyz_parser_matches_python_float(tmp_path):
+    """amofb_xyz_parse (host code of libamofb.so): every decimal string becomes the double Python's float() gives -- including
+    17-digit values, halfway cases, subnormals, '+' signs and Fortran D exponents --, extended-XYZ column layouts are honoured,
+    and malformed input is refused with the frame named."""
+    from amof_b200 import _lib, stream
+    rng = np.random.default_rng(11)
+    tricky = ["0.1", "-0.30000000000000004", "1e23", "8.5e-324", "2.2250738585072011e-308", "9007199254740993", "+1.5",
+              "1.0D+01", "-2.5d-3", "123456789012345678901234567890.5", "0.500000000000000166533453693773481063544750213623046875",
+              "1.7976931348623157e308", ".5", "5.", "1E5", "-0.0"]
+    n = 40
+    vals = [repr(float(x)) for x in rng.standard_normal(3 * n * 3) * 10.0 ** rng.integers(-8, 9, 3 * n * 3)]
+    vals[:len(tricky)] = tricky
+    frames = []
+    for f in range(3):
+        lines = ["%d" % n, "frame %d" % f]
+        for a in range(n):
+            x, y, z = vals[(f * n + a) * 3:(f * n + a) * 3 + 3]
+            lines.append(" %s\t%s   %s %s  extra" % ("Zn" if a % 2 else "N", x, y, z))
+        frames.append("\n".join(lines) + "\n")
+    text = "".join(frames).encode()
+    off = np.cumsum([0] + [len(f) for f in frames])
+    out = np.zeros((3, n, 3))
+    sym = bytearray(8 * n)
+    _lib.xyz_parse(text, off, n, 1, sym, False, out, threads=2)
+    want = np.array([float(v.replace("D", "e").replace("d", "e")) for v in vals]).reshape(3, n, 3)
+    assert np.array_equal(out.view(np.uint64), want.view(np.uint64))
+    assert bytes(sym[:8]) == b"N\0\0\0\0\0\0\0" and bytes(sym[8:16]) == b"Zn\0\0\0\0\0\0"
+    # a frame whose atom order changes, a truncated frame and a non-number are refused, with the frame named
+    for bad_text in (text.replace(b"frame 2\n N", b"frame 2\n O"), text[:-40] + b"\n" * 0, text.replace(b"extra\n", b"\n").replace(b"0.1", b"0.1x")):
+        with pytest.raises(ValueError, match="frame"):
+            o2 = off.copy()
+            o2[-1] = len(bad_text)
+            _lib.xyz_parse(bad_text, o2, n, 1, bytearray(sym), True, np.zeros((3, n, 3)), threads=1)
+    # extended XYZ with the positions after another column
+    p = tmp_path / "cols.xyz"
+    with open(p, "w") as fh:
+        for f in range(2):
+            fh.write('3\nLattice="5 0 0 0 5 0 0 0 5" Properties=species:S:1:tag:I:1:pos:R:3\n')
+            for a, s in enumerate(("Zn", "N", "N")):
+                fh.write("%s %d %r %r %r\n" % (s, a, 0.1 * a + f, 0.2, 0.3 * a))
+    s = stream.XyzStream(str(p))
+    assert s._pos_col == 2 and np.array_equal(s[1].get_positions(), [[1.0, 0.2, 0.0], [0.1 * 1 + 1, 0.2, 0.3], [0.1 * 2 + 1, 0.2, 0.3 * 2]])

@@ -1,5 +1,5 @@
 """File -> result throughput: a C2 trajectory written as extended XYZ, analysed through amof_b200.stream.XyzStream
-(chunks parsed by a few threads into page-locked buffers while the GPU counts) against the same frames already in memory.
+(chunks parsed by the native amofb_xyz_parse on all host cores into page-locked buffers while the GPU counts) against the same frames already in memory.
     python tools/profile_stream.py [frames] [threads]"""
 import os
 import sys
