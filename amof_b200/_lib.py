@@ -57,6 +57,7 @@ SIGNATURES = {
     "amofb_pair_push": (C.c_int, [_vp, C.c_int, _vp, _dp]),
     "amofb_pair_push_device": (C.c_int, [_vp, C.c_int, _vp, _dp]),
     "amofb_pair_finish": (C.c_int, [_vp, _u64p, _u64p, C.c_int64, _i64p, _dp]),
+    "amofb_pair_take": (C.c_int, [_vp, _u64p, _u64p, C.c_int64, _i64p, _dp]),
     "amofb_rdf_begin": (C.c_int, [_vp, C.c_int, C.c_int, _u8p, C.c_double, C.c_int]),
     "amofb_rdf_push": (C.c_int, [_vp, C.c_int, _vp, _dp]),
     "amofb_rdf_finish": (C.c_int, [_vp, _u64p, _i64p, _dp]),
@@ -88,6 +89,7 @@ SIGNATURES = {
     "amofb_msd_direct": (C.c_int, [_vp, _dp]),
     "amofb_msd_get_positions": (C.c_int, [_vp, _dp]),
     "amofb_msd_end": (C.c_int, [_vp]),
+    "amofb_guard_violations": (C.c_int64, [_vp]),
     "amofb_xyz_index": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _i64p, C.c_int64, _i64p, _i64p]),
     "amofb_xyz_parse": (C.c_int, [C.c_char_p, _i64p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
 }
@@ -246,6 +248,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.amofb_launch_count(self.h))
 
+    def guard_violations(self):
+        """pooled device blocks found written out of bounds (AMOFB_GUARD=1 at context creation), -1 when the guard is off"""
+        return int(self.lib.amofb_guard_violations(self.h))
+
     def set_option(self, option, value):
         """amofb_set_option: option names are the AMOFB_OPT_* constants of include/amofb.h"""
         self.check(self.lib.amofb_set_option(self.h, int(option), int(value)))
@@ -305,6 +311,23 @@ class GpuBackend:
         ctx.check(lib.amofb_pair_finish(ctx.h, None if hist is None else _ptr(hist, _u64p),
                                         None if cn is None else _ptr(cn, _u64p), total, C.byref(nf), C.byref(vs)))
         return {"hist": hist, "cn": cn, "n_frames": int(nf.value), "volume_sum": float(vs.value)}
+
+    def pair_counts_each(self, species, n_species, chunks, rmax, nbins):
+        """One RDF histogram PER CHUNK (generator of pair_counts-like dicts): one analysis stays open and is emptied after each
+        chunk (amofb_pair_take), instead of a begin/finish pair per frame."""
+        ctx, lib = self.ctx, self.ctx.lib
+        species = np.ascontiguousarray(species, dtype=np.uint8)
+        S = int(n_species)
+        ctx.check(lib.amofb_pair_begin(ctx.h, len(species), S, _ptr(species, _u8p), float(rmax), int(nbins), None))
+        try:
+            for chunk in chunks:
+                self._push_all(lib.amofb_pair_push, lib.amofb_pair_push_device, [chunk], len(species))
+                hist = np.zeros((S, S, int(nbins)), dtype=np.uint64)
+                nf, vs = C.c_int64(0), C.c_double(0.0)
+                ctx.check(lib.amofb_pair_take(ctx.h, _ptr(hist, _u64p), None, 0, C.byref(nf), C.byref(vs)))
+                yield {"hist": hist, "cn": None, "n_frames": int(nf.value), "volume_sum": float(vs.value)}
+        finally:
+            lib.amofb_pair_finish(ctx.h, None, None, 0, None, None)
 
     def _push_all(self, push_host, push_device, chunks, n_atoms):
         ctx = self.ctx

@@ -41,6 +41,8 @@ extern "C" int amofb_create(int device, amofb_ctx **out) {
         delete ctx;
         return AMOFB_ERR_CUDA;
     }
+    const char *g = getenv("AMOFB_GUARD");
+    ctx->guard = g && *g && *g != '0';
     *out = ctx;
     return AMOFB_OK;
 }
@@ -98,6 +100,7 @@ extern "C" int amofb_sync_copies(amofb_ctx *ctx) {
 }
 
 extern "C" int64_t amofb_launch_count(const amofb_ctx *ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int64_t amofb_guard_violations(const amofb_ctx *ctx) { return ctx ? (ctx->guard ? ctx->guard_violations : -1) : -1; }
 
 extern "C" int amofb_set_option(amofb_ctx *ctx, int option, int value) {
     if (!ctx) return AMOFB_ERR_ARG;
@@ -189,13 +192,47 @@ extern "C" int amofb_memcpy_d2h(amofb_ctx *ctx, void *dst_host, const void *src_
     return AMOFB_OK;
 }
 
+// AMOFB_GUARD (the pool's compute-sanitizer is closed, profiles/r02_sanitizer_refused.log): POOL_GUARD canary bytes before and
+// after every pooled device block, compared when the block comes back; a block is only reused at its exact size
+static int pool_guard_alloc(amofb_ctx *ctx, PoolBlock &blk) {
+    char *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, blk.bytes + 2 * POOL_GUARD);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? (cudaGetLastError(), AMOFB_ERR_MEMORY) : AMOFB_ERR_CUDA;
+    cudaMemset(base, 0xA5, POOL_GUARD);
+    cudaMemset(base + POOL_GUARD + blk.bytes, 0xA5, POOL_GUARD);
+    blk.p = base + POOL_GUARD;
+    blk.guarded = true;
+    return AMOFB_OK;
+}
+static void pool_guard_check(amofb_ctx *ctx, const PoolBlock &blk) {
+    if (!blk.guarded) return;
+    static unsigned char h[2 * POOL_GUARD];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, (char *)blk.p - POOL_GUARD, POOL_GUARD, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h + POOL_GUARD, (char *)blk.p + blk.bytes, POOL_GUARD, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < 2 * POOL_GUARD; ++i)
+        if (h[i] != 0xA5) {
+            ++ctx->guard_violations;
+            fprintf(stderr, "amofb guard: block of %zu bytes written %s its bounds (byte %d of the canary)\n", blk.bytes,
+                    i < POOL_GUARD ? "before" : "after", i < POOL_GUARD ? POOL_GUARD - i : i - POOL_GUARD);
+            cudaMemset((char *)blk.p - POOL_GUARD, 0xA5, POOL_GUARD);
+            cudaMemset((char *)blk.p + blk.bytes, 0xA5, POOL_GUARD);
+            break;
+        }
+}
+static void pool_block_free(const PoolBlock &b) {
+    if (b.pinned) cudaFreeHost(b.p);
+    else cudaFree(b.guarded ? (char *)b.p - POOL_GUARD : (char *)b.p);
+}
+
 static int pool_get(amofb_ctx *ctx, void **out, size_t bytes, bool pinned) {
     *out = nullptr;
     if (bytes < 256) bytes = 256;
+    const bool guarded = ctx->guard && !pinned;
     int best = -1;
     for (int i = 0; i < (int)ctx->pool_idle.size(); ++i) {
         const PoolBlock &b = ctx->pool_idle[i];
-        if (b.pinned == pinned && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 &&
+        if (b.pinned == pinned && b.bytes >= bytes && (guarded ? b.bytes == bytes : b.bytes <= 2 * bytes + 4096) &&
             (best < 0 || b.bytes < ctx->pool_idle[best].bytes))
             best = i;
     }
@@ -203,6 +240,16 @@ static int pool_get(amofb_ctx *ctx, void **out, size_t bytes, bool pinned) {
     if (best >= 0) {
         blk = ctx->pool_idle[best];
         ctx->pool_idle.erase(ctx->pool_idle.begin() + best);
+    } else if (guarded) {
+        blk.bytes = bytes;
+        blk.pinned = false;
+        int rc = pool_guard_alloc(ctx, blk);
+        if (rc == AMOFB_ERR_MEMORY) {
+            for (auto &b : ctx->pool_idle) pool_block_free(b);
+            ctx->pool_idle.clear();
+            rc = pool_guard_alloc(ctx, blk);
+        }
+        if (rc) return amofb_fail(ctx, rc, "guarded device allocation of %zu bytes failed", bytes);
     } else {
         blk.bytes = bytes;
         blk.pinned = pinned;
@@ -210,7 +257,7 @@ static int pool_get(amofb_ctx *ctx, void **out, size_t bytes, bool pinned) {
         if (e == cudaErrorMemoryAllocation) {
             // give idle blocks back to the driver and retry once
             cudaGetLastError();
-            for (auto &b : ctx->pool_idle) { if (b.pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+            for (auto &b : ctx->pool_idle) pool_block_free(b);
             ctx->pool_idle.clear();
             e = pinned ? cudaHostAlloc(&blk.p, bytes, cudaHostAllocDefault) : cudaMalloc(&blk.p, bytes);
         }
@@ -230,14 +277,15 @@ static void pool_put(amofb_ctx *ctx, void *p) {
     if (!p) return;
     auto it = ctx->pool_live.find(p);
     if (it == ctx->pool_live.end()) return;
+    pool_guard_check(ctx, it->second);
     ctx->pool_idle.push_back(it->second);
     ctx->pool_live.erase(it);
 }
 
 static void pool_destroy(amofb_ctx *ctx) {
-    for (auto &kv : ctx->pool_live) ctx->pool_idle.push_back(kv.second);
+    for (auto &kv : ctx->pool_live) { pool_guard_check(ctx, kv.second); ctx->pool_idle.push_back(kv.second); }
     ctx->pool_live.clear();
-    for (auto &b : ctx->pool_idle) { if (b.pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+    for (auto &b : ctx->pool_idle) pool_block_free(b);
     ctx->pool_idle.clear();
 }
 
@@ -754,18 +802,22 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
 }
 
 extern "C" int amofb_pair_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell) {
+    nvtx_range rng("amofb_pair_push");
     return pair_push_impl(ctx, n_frames, pos, false, cell);
 }
 extern "C" int amofb_pair_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell) {
+    nvtx_range rng("amofb_pair_push_device");
     return pair_push_impl(ctx, n_frames, pos_device, true, cell);
 }
 
-extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
-                                 int64_t *n_frames_out, double *volume_sum_out) {
+// finish and take share this: drain the batches and hand out what has accumulated; `reset` empties the accumulators and
+// keeps the analysis open (amof.rdf.CoordinationNumber wants one histogram per frame, rdf.py:181-186)
+static int pair_collect(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames, int64_t *n_frames_out,
+                        double *volume_sum_out, bool reset) {
     if (!ctx) return AMOFB_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     PairState *p = ctx->pair;
-    if (!p) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_pair_finish before amofb_pair_begin");
+    if (!p) return amofb_fail(ctx, AMOFB_ERR_STATE, "amofb_pair_finish / _take before amofb_pair_begin");
     int rc = AMOFB_OK;
     auto body = [&]() -> int {
         Batcher &b = p->bt;
@@ -809,12 +861,32 @@ extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_co
         }
         if (n_frames_out) *n_frames_out = b.frames_seen;
         if (volume_sum_out) *volume_sum_out = b.volume_sum;
+        if (reset) {
+            const size_t hist_n = (size_t)p->nkeys * p->nbins;
+            if (hist_n) CUDA_TRY(ctx, cudaMemsetAsync(p->d_hist, 0, sizeof(unsigned long long) * hist_n, ctx->s_compute));
+            if (p->d_slabs)
+                CUDA_TRY(ctx, cudaMemsetAsync(p->d_slabs, 0, sizeof(unsigned long long) * hist_n * std::max(p->grid, p->tile_grid), ctx->s_compute));
+            b.frames_seen = 0;
+            b.volume_sum = 0.0;
+            b.out_all.clear();
+        }
         return AMOFB_OK;
     };
     rc = body();
     if (ctx->profiling) drain_pair_events(ctx);
-    pair_release(ctx);
+    if (!reset || rc) pair_release(ctx);
     return rc;
+}
+
+extern "C" int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
+                                 int64_t *n_frames_out, double *volume_sum_out) {
+    nvtx_range rng("amofb_pair_finish");
+    return pair_collect(ctx, hist, cn_counts, cn_frames, n_frames_out, volume_sum_out, false);
+}
+extern "C" int amofb_pair_take(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
+                               int64_t *n_frames_out, double *volume_sum_out) {
+    nvtx_range rng("amofb_pair_take");
+    return pair_collect(ctx, hist, cn_counts, cn_frames, n_frames_out, volume_sum_out, true);
 }
 
 extern "C" int amofb_rdf_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species, double rmax, int nbins) {

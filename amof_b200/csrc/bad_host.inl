@@ -257,13 +257,16 @@ static int bad_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool o
 }
 
 extern "C" int amofb_bad_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell) {
+    nvtx_range rng("amofb_bad_push");
     return bad_push_impl(ctx, n_frames, pos, false, cell);
 }
 extern "C" int amofb_bad_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell) {
+    nvtx_range rng("amofb_bad_push_device");
     return bad_push_impl(ctx, n_frames, pos_device, true, cell);
 }
 
 extern "C" int amofb_bad_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *dropped, int64_t *n_frames_out) {
+    nvtx_range rng("amofb_bad_finish");
     if (!ctx) return AMOFB_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     BadState *p = ctx->bad;

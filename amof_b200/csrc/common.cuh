@@ -43,7 +43,9 @@ struct PoolBlock {
     void *p;
     size_t bytes;
     bool pinned;
+    bool guarded = false;   // AMOFB_GUARD: p sits POOL_GUARD bytes inside the allocation, canaries on both sides
 };
+#define POOL_GUARD 4096
 
 struct amofb_ctx {
     int device = 0;
@@ -59,6 +61,8 @@ struct amofb_ctx {
     std::vector<double> tthr_cache;
     std::vector<PoolBlock> pool_idle;
     std::unordered_map<void *, PoolBlock> pool_live;
+    bool guard = false;            // AMOFB_GUARD=1: canary bytes around every pooled device block, checked when it is returned
+    int64_t guard_violations = 0;
     cudaStream_t s_compute = nullptr;
     cudaStream_t s_copy = nullptr;
     std::string err;

@@ -285,19 +285,42 @@ class CoordinationNumber(object):
         bins = int(rmax // dr)
         r = np.arange(bins) * dr
         rows = []
-        for i in range(len(trajectory)):
-            atom = trajectory[i]
-            # a fresh accumulator per frame, like the reference's per-frame RadialDistributionFunction (rdf.py:181)
-            zs, spec, res = pair_histograms([atom], float(rmax), bins, distributed=False)
-            n_of = np.bincount(spec, minlength=len(zs))
-            idx = {z: k for k, z in enumerate(zs)}
-            density = len(atom) / atom.get_volume()
-            dic = {'Step': step[i]}
-            for nn_set, cutoff in nb_set_and_cutoff.items():
-                a, b = tuple(_atomic_numbers[s] for s in nn_set.split('-'))
-                g = normalise_counts(res["hist"][idx[a], idx[b]], n_of[idx[a]], 1, len(spec), res["volume_sum"], rmax)
-                dic[nn_set] = get_coordination_number(r, g, cutoff, density)
-            rows.append(dic)
+        T = len(trajectory)
+        if T == 0:
+            self.data = pd.DataFrame(rows)
+            return
+        backend = _lib.get_backend()
+        numbers = np.asarray(frames._numbers_of(trajectory[0]))
+        zs, spec = frames.species_index(numbers)
+        frames.check_same_atoms(trajectory, numbers, 0, T)
+        n_of = np.bincount(spec, minlength=len(zs))
+        idx = {z: k for k, z in enumerate(zs)}
+        ctx = getattr(backend, "ctx", None)
+        if ctx is not None:
+            ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, 1 if CONVENTIONS["bin_rule"] == "multiply" else 0)
+
+        def single_frames():
+            for i in range(T):
+                atom = trajectory[i]
+                yield (np.asarray(atom.get_positions(), dtype=np.float64)[None], np.asarray(atom.get_cell(), dtype=np.float64)[None])
+
+        # a fresh histogram per frame, like the reference's per-frame RadialDistributionFunction (rdf.py:181); ONE analysis stays
+        # open on the GPU and is emptied after every frame
+        each = backend.pair_counts_each(spec, len(zs), single_frames(), float(rmax), bins)
+        try:
+            for i, res in enumerate(each):
+                atom = trajectory[i]
+                density = len(atom) / atom.get_volume()
+                dic = {'Step': step[i]}
+                for nn_set, cutoff in nb_set_and_cutoff.items():
+                    a, b = tuple(_atomic_numbers[s] for s in nn_set.split('-'))
+                    g = normalise_counts(res["hist"][idx[a], idx[b]], n_of[idx[a]], 1, len(spec), res["volume_sum"], rmax)
+                    dic[nn_set] = get_coordination_number(r, g, cutoff, density)
+                rows.append(dic)
+        finally:
+            each.close()            # ends the open analysis if the loop was left early
+            if ctx is not None:
+                ctx.set_option(_lib.AMOFB_OPT_RDF_BIN_RULE, 0)
         self.data = pd.DataFrame(rows)
 
     @classmethod

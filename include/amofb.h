@@ -56,6 +56,10 @@ int amofb_sync(amofb_ctx *ctx);
 int amofb_sync_copies(amofb_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py reports it as gpu_launches). */
 int64_t amofb_launch_count(const amofb_ctx *ctx);
+/* Debug aid.  With AMOFB_GUARD=1 in the environment at amofb_create every pooled device block carries 4 KiB of canary bytes on
+ * either side, compared when the block is returned; this is how many blocks were found written out of bounds so far (each is
+ * also reported on stderr).  -1 when the guard is off. */
+int64_t amofb_guard_violations(const amofb_ctx *ctx);
 /* Conventions of the upstream packages that cannot be read off their sources here (asap3 / ase are not on disk,
  * SURVEY.md 8(c) U1-U6) are options with the oracle's pin as default:
  *   AMOFB_OPT_RDF_BIN_RULE  0: bin = (int)(d / (rMax/nBins))   (default, pin U1)
@@ -101,11 +105,16 @@ int amofb_memcpy_d2h(amofb_ctx *ctx, void *dst_host, const void *src_device, uin
  *                    cn_frames must equal the number of frames pushed
  *         n_frames_out, volume_sum_out: frames seen and the sum of their cell volumes
  *         finish ends the accumulation; begin may be called again on the same ctx.
+ * take  : finish's outputs for the frames pushed since begin (or since the last take), after which the accumulators are
+ *         empty and the analysis stays OPEN: one histogram per frame, as amof.rdf.CoordinationNumber builds a fresh
+ *         RadialDistributionFunction for every frame (/root/reference/amof/rdf.py:181-186), without re-planning.
  */
 int amofb_pair_begin(amofb_ctx *ctx, int n_atoms, int n_species, const uint8_t *species,
                      double rmax, int nbins, const double *cn_cutoff);
 int amofb_pair_push(amofb_ctx *ctx, int n_frames, const double *pos, const double *cell);
 int amofb_pair_push_device(amofb_ctx *ctx, int n_frames, const double *pos_device, const double *cell);
+int amofb_pair_take(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
+                    int64_t *n_frames_out, double *volume_sum_out);
 int amofb_pair_finish(amofb_ctx *ctx, uint64_t *hist, uint64_t *cn_counts, int64_t cn_frames,
                       int64_t *n_frames_out, double *volume_sum_out);
 

@@ -32,6 +32,10 @@ class OracleBackend:
         cn = (np.array(cn, dtype=np.uint64).reshape(nf, S, S) if cn_cutoff is not None else None)
         return {"hist": hist, "cn": cn, "n_frames": nf, "volume_sum": vs}
 
+    def pair_counts_each(self, species, n_species, chunks, rmax, nbins):
+        for chunk in chunks:
+            yield self.pair_counts(species, n_species, [chunk], rmax=rmax, nbins=nbins)
+
     def bad_counts(self, species, n_species, chunks, cutoff, triples, dtheta, nbins):
         hist = np.zeros((len(triples), 33, int(nbins)), dtype=np.uint64)
         dropped = np.zeros(len(triples), dtype=np.uint64)

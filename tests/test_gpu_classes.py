@@ -162,3 +162,27 @@ def test_streamed_file_matches_in_memory(backend, tmp_path):
     b1 = amof_b200.bad.Bad.from_trajectory(s, {'Zn-N': 2.5})
     b2 = amof_b200.bad.Bad.from_trajectory(traj, {'Zn-N': 2.5})
     assert np.array_equal(b1.counts["N-Zn-N"], b2.counts["N-Zn-N"])
+
+
+def test_rdf_coordination_number_per_frame_take(backend):
+    """amof.rdf.CoordinationNumber (rdf.py:135-214) integrates ONE histogram per frame: here a single analysis stays open and
+    amofb_pair_take empties it after every frame.  Each frame's histogram must equal the one a separate analysis of that frame
+    gives, on the default dr = 1e-4 (global-memory histograms) and on a coarse dr (shared-memory histograms)."""
+    traj = small_traj(4, sigma=0.12)
+    zs, spec = frames.species_index(traj[0].get_atomic_numbers())
+    for rmax, bins in ((2.5, 24999), (6.0, 300)):
+        chunks = [(t.get_positions()[None], np.asarray(t.get_cell())[None]) for t in traj]
+        each = list(backend.pair_counts_each(spec, len(zs), iter(chunks), rmax, bins))
+        assert len(each) == 4
+        for k, res in enumerate(each):
+            want, _ = orc.rdf_traj(chunks[k][0], chunks[k][1], spec, len(zs), rmax, bins)
+            assert res["n_frames"] == 1 and np.array_equal(res["hist"], want)
+            assert res["volume_sum"] == abs(np.linalg.det(chunks[k][1][0]))
+    sets = {"Zn-N": 2.5, "C-N": 1.728}
+    got = amof_b200.rdf.CoordinationNumber.from_trajectory(traj, sets, dr=0.001, delta_Step=5).data
+    assert list(got.columns) == ["Step", "Zn-N", "C-N"] and list(got["Step"]) == [0, 5, 10, 15]
+    for k in range(4):
+        one = amof_b200.rdf.CoordinationNumber.from_trajectory([traj[k]], sets, dr=0.001).data
+        assert got["Zn-N"][k] == one["Zn-N"][0] and got["C-N"][k] == one["C-N"][0]
+    # the analysis was closed: the next one opens normally
+    amof_b200.rdf.Rdf.from_trajectory(traj, dr=0.05, rmax=5.0)
