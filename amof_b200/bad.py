@@ -12,6 +12,12 @@ Deviation: when the neighbour-set keys cover every species of the
 pseudo-species "X" and then crashes on ``ase.data.chemical_symbols["X"]`` (bad.py:111,127).  Here the X columns
 ("X-A-X": any neighbours around A; "X-X-X": any neighbours around any atom) are computed as the docstring of
 ``bad_BAB`` describes instead of raising.
+
+Deviation (minimum image): ``get_angles(mic=True)`` re-derives the two bond vectors from the atom INDICES with the minimum
+image convention, so a neighbour found through a farther periodic image is measured along its nearest image instead
+(bad.py:113, ase/atoms.py get_angles).  libamofb measures the image the neighbour list found.  The two agree whenever
+every cutoff is below half the smallest perpendicular cell height -- then the nearest image is the only one under the
+cutoff --, and ``amofb_bad_begin`` refuses any other request (AMOFB_ERR_GEOMETRY -> ValueError) rather than differ silently.
 """
 import logging
 

@@ -730,6 +730,198 @@ __device__ __forceinline__ void msd_soa_tile(const double *__restrict__ sm, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide register tiles for the autocorrelation form (round 2, second design).  ncu of k_msd_window_soa<8,13,true>: DFMA is 30 % of
+// the executed instructions, the shared-memory pipe is busier (49 %) than the FP64 pipe (32 %), 3.4 barrier-stall cycles per
+// instruction.  Three changes:
+//   * ONE tile covers all the windows of a pass (NWT up to 32 sums per thread) and KB = 6 / 8 / 10 frames: the partners of the
+//     windows 0 .. KB-1 ARE the thread's own frames, so a full tile costs NWT - 1 + KB shared-memory reads for KB (NWT - 1)
+//     products (10 x 24 products on 34 reads at C5, against 8 x 13 on 28);
+//   * no remainder tiles and no per-partner bounds test in the steady state: the series is followed by zeros up to the end of
+//     the last super-row (a zero frame adds nothing to a sum of products), tiles whose partners all exist run the unchecked
+//     body, the others stop at the first partner before frame 1 (frame 0 is the origin: exactly zero);
+//   * two series buffers: the bulk copy of the next component is in flight while this one is worked on, and a block never
+//     waits at a barrier for data.
+__device__ __forceinline__ double msd_lds(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// sb: shared byte address of frame b of the series; d8 = 8 delta; lag8 = 8 wlo delta; partner slot v is frame b + (v - wlo) delta
+// and exists iff v >= -e (e = s KB - wlo)
+template <int KB, int NWT, bool WLO0, bool FULL>
+__device__ __forceinline__ void msd_wide_tile(unsigned sb, int d8, int lag8, int e, double (&acc)[NWT]) {
+    double kv[KB];
+#pragma unroll
+    for (int i = 0; i < KB; ++i) kv[i] = msd_lds(sb + (unsigned)(i * d8));
+#pragma unroll
+    for (int v = KB - 1; v > -NWT; --v) {
+        if (!FULL && (!WLO0 || v < 0) && v < -e) break;
+        double pv;
+        if (WLO0 && v >= 0) pv = kv[v];
+        else pv = msd_lds(sb + (unsigned)(v * d8 - lag8));
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+            const int t = i - v;
+            if (t >= (WLO0 ? 1 : 0) && t < NWT) acc[t] = __fma_rn(kv[i], pv, acc[t]);      // window 0 is returned as exactly zero
+        }
+    }
+}
+
+#define MSD_WIDE_THREADS 256
+#define MSD_WIDE_NWT_MAX 32
+
+// partial[block][2][S][nw] as k_msd_window_soa<.., true>: [0] sum of R_k . R_{k-m}, [1] sum of |R_k|^2 + |R_{k-m}|^2.
+// rowcap: doubles per series buffer (tp + the zero tail, even).  pieces[pass][threads + 1]: frame ranges for the sums of squares
+// of a pass -- thread t adds up the frames [pieces[t], pieces[t+1]) of every series; no range straddles m + 1 or T - m for a
+// window length m of the pass, so  sum_{k=m+1}^{T-1} v_k^2 + sum_{j=1}^{T-1-m} v_j^2  is a sum of whole ranges.
+// Dynamic shared memory: 2 rowcap | 2 S nw | nwarp NWT | threads.
+//
+// No block-wide barrier in the steady state: a warp waits for a series on the buffer's mbarrier, works through its tiles, and
+// counts itself out of the buffer; the last warp out issues the bulk copy of the series after next into it.  Warps drift up to
+// one series apart, and the thread -> task map is mirrored on odd series, so that a thread with the short (early-frame) tiles on
+// one series has the long ones on the next: the per-series imbalance (tiles near frame 0 have few partners) evens out.
+template <int KB, int NWT>
+__global__ void __launch_bounds__(MSD_WIDE_THREADS, 2) k_msd_window_wide(const double *__restrict__ P, const uint8_t *__restrict__ species,
+                                                                         const int *__restrict__ perm, const int *__restrict__ pieces,
+                                                                         int n, int T, int tp, int delta, int nw, int S, int rowcap,
+                                                                         double *__restrict__ partial) {
+    extern __shared__ __align__(16) double sm[];
+    double *s_acc = sm + 2 * (size_t)rowcap;                // [S][nw]
+    double *s_ss = s_acc + (size_t)S * nw;                  // [S][nw]
+    double *s_red = s_ss + (size_t)S * nw;                  // [nwarp][NWT]
+    double *s_part = s_red + (size_t)NWT * (MSD_WIDE_THREADS / 32);      // [threads]: sums of squares per range
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    __shared__ unsigned s_done[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * S * nw; i += blockDim.x) s_acc[i] = 0.0;      // s_acc and s_ss are adjacent
+    for (int b = 0; b < 2; ++b)                                                     // the zero tails (never written again)
+        for (int i = tp + threadIdx.x; i < rowcap; i += blockDim.x) sm[(size_t)b * rowcap + i] = 0.0;
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&s_mbar[0]);
+    const unsigned sm_addr = (unsigned)__cvta_generic_to_shared(sm);
+    if (threadIdx.x == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); s_done[0] = 0u; s_done[1] = 0u; }
+    __syncthreads();
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int a_lo = min(n, blockIdx.x * per), a_hi = min(n, a_lo + per);
+    const int nrow = 3 * (a_hi - a_lo);
+    const int span = KB * delta;
+    const int nsr = (T - 2 + span) / span;                  // super-rows over k = 1 .. T-1, the last one zero-filled
+    const int ntask = nsr * delta;
+    const unsigned row_bytes = 8u * (unsigned)tp;
+    const int d8 = 8 * delta;
+    // this thread's tasks q = q0, q0 + blockDim, ...: (super-row s, residue r), stepped without a division; q0 = tid on even
+    // series and blockDim - 1 - tid on odd ones
+    const int qe = (int)threadIdx.x, qo = (int)blockDim.x - 1 - (int)threadIdx.x;
+    const int se_first = qe / delta, re_first = qe - se_first * delta;
+    const int so_first = qo / delta, ro_first = qo - so_first * delta;
+    const int s_step = (int)blockDim.x / delta, r_step = (int)blockDim.x - s_step * delta;
+    auto issue = [&](int row) {                             // one thread: bulk copy of series `row` of the block into buffer row & 1
+        const int a = perm[a_lo + row / 3];
+        const char *src = reinterpret_cast<const char *>(P + ((size_t)a * 3 + (size_t)(row % 3)) * tp);
+        const unsigned dst = sm_addr + (unsigned)(row & 1) * 8u * (unsigned)rowcap, mb = mbar0 + 8u * (unsigned)(row & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(mb, row_bytes);
+        for (unsigned o = 0; o < row_bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, row_bytes - o), mb);
+    };
+    for (int w0 = 0, pass = 0; w0 < nw; w0 += NWT, ++pass) {
+        const int lag8 = w0 * d8;
+        const int pk0 = pieces[(size_t)pass * (blockDim.x + 1) + threadIdx.x], pk1 = pieces[(size_t)pass * (blockDim.x + 1) + threadIdx.x + 1];
+        double acc[NWT];
+#pragma unroll
+        for (int w = 0; w < NWT; ++w) acc[w] = 0.0;
+        double sq = 0.0;
+        int cur_sp = -1;
+        if (threadIdx.x == 0) {                             // both buffers are free: the previous pass ended with a barrier
+            if (nrow > 0) issue(0);
+            if (nrow > 1) issue(1);
+        }
+        for (int row = 0; row <= nrow; ++row) {
+            if (row % 3 == 0) {
+                // the block's atoms are visited in species order (perm: a stable sort of [a_lo, a_hi) by species), so the register
+                // sums are reduced at most S times per pass.  Every thread gets here at the same series: the barriers match.
+                const int sp = row < nrow ? (int)species[perm[a_lo + row / 3]] : -2;
+                if (sp != cur_sp) {
+                    if (cur_sp >= 0) {
+#pragma unroll
+                        for (int w = 0; w < NWT; ++w) {
+                            double v = acc[w];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                            if (lane == 0) s_red[warp * NWT + w] = v;
+                            acc[w] = 0.0;
+                        }
+                        s_part[threadIdx.x] = sq;
+                        sq = 0.0;
+                        __syncthreads();
+                        if ((int)threadIdx.x < NWT && w0 + (int)threadIdx.x < nw) {
+                            const int wi = w0 + (int)threadIdx.x, m = wi * delta;
+                            double t = 0.0;
+                            for (int q = 0; q < nwarp; ++q) t += s_red[q * NWT + threadIdx.x];
+                            s_acc[cur_sp * nw + wi] += t;
+                            if (wi > 0 && m < T - 1) {
+                                double ss = 0.0;            // whole ranges: k >= m + 1 (the later frame of a pair), k <= T - 1 - m (the earlier one)
+                                const int *pk = pieces + (size_t)pass * (blockDim.x + 1);
+                                for (int q = 0; q < (int)blockDim.x; ++q) {
+                                    const int k0 = pk[q], k1 = pk[q + 1];
+                                    if (k1 > k0) {
+                                        const double v = s_part[q];
+                                        if (k0 >= m + 1) ss += v;
+                                        if (k1 <= T - m) ss += v;
+                                    }
+                                }
+                                s_ss[cur_sp * nw + wi] += ss;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    cur_sp = sp;
+                }
+            }
+            if (row >= nrow) break;
+            const int b = row & 1;
+            {   // completed phases of buffer b before this series: those of this pass with its parity, plus all of the earlier passes
+                const int before = (row >> 1) + pass * ((nrow + 1 - b) >> 1);
+                mbar_wait(mbar0 + 8u * (unsigned)b, (unsigned)(before & 1));
+            }
+            const unsigned xb = sm_addr + (unsigned)b * 8u * (unsigned)rowcap;
+            const double *x = sm + (size_t)b * rowcap;
+            for (int k = pk0; k < pk1; ++k) sq = __fma_rn(x[k], x[k], sq);
+            int sq_ = b ? so_first : se_first, r = b ? ro_first : re_first;
+            for (int q = b ? qo : qe; q < ntask; q += blockDim.x) {
+                const int e = sq_ * KB - w0;
+                const unsigned sb = xb + 8u * (unsigned)(1 + sq_ * span + r);
+                if (e > -KB) {
+                    // a warp whose lanes are not all in the unchecked case runs the checked body for all of them (one code path)
+                    const bool full = __all_sync(__activemask(), e >= NWT - 1);
+                    if (full) {
+                        if (w0 == 0) msd_wide_tile<KB, NWT, true, true>(sb, d8, lag8, e, acc);
+                        else msd_wide_tile<KB, NWT, false, true>(sb, d8, lag8, e, acc);
+                    } else {
+                        if (w0 == 0) msd_wide_tile<KB, NWT, true, false>(sb, d8, lag8, e, acc);
+                        else msd_wide_tile<KB, NWT, false, false>(sb, d8, lag8, e, acc);
+                    }
+                }
+                sq_ += s_step; r += r_step;
+                if (r >= delta) { r -= delta; ++sq_; }
+            }
+            // this warp has left buffer b; the last warp out refills it with the series after next
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&s_done[b], 1u) == (unsigned)(nwarp - 1)) {
+                    s_done[b] = 0u;
+                    __threadfence_block();
+                    if (row + 2 < nrow) issue(row + 2);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * S * nw; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * S * nw + i] = s_acc[i];
+}
+
 // P: prepared series, atom-major, three arrays of tp doubles per atom.  Window lengths 0, delta, 2 delta, ...
 // partial[block][2][S][nw]: [0] the pair sums (cross terms when DOT, squared differences otherwise), [1] when DOT the
 // sums of |R_k|^2 + |R_{k-m}|^2 over the same pairs; the caller forms [1] - 2 [0].

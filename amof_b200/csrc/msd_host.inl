@@ -97,6 +97,8 @@ extern "C" int amofb_msd_begin(amofb_ctx *ctx, int n_frames, int n_atoms, const 
         if ((rc = dev_alloc(ctx, &p->d_stage[i], (size_t)p->stage_frames * n_atoms * 3))) return fail(rc);
         cudaEventCreateWithFlags(&p->ev_stage[i], cudaEventDisableTiming);
     }
+    if (p->Tp > p->T)           // the pad frame of every series (T odd): the window kernels copy whole series and rely on zeros after frame T-1
+        cudaMemset2D(p->d_P + p->T, sizeof(double) * (size_t)p->Tp, 0, sizeof(double), 3 * (size_t)n_atoms);
     cudaMemcpy(p->d_geom, geom.data(), sizeof(MsdGeom) * geom.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_masses, masses, sizeof(double) * n_atoms, cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_species, species, (size_t)n_atoms, cudaMemcpyHostToDevice);
@@ -539,9 +541,37 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
     if (env_int("AMOFB_MSD_DEBUG", 0)) fprintf(stderr, "[amofb msd] window kernel shape: %d sums per thread, %d groups, %d warps per group (%d threads)\n", ap_nwt, ap_ng, threads / 32 / ap_ng, threads);
     const size_t smem = sizeof(double) * ((size_t)p->Tp + 2 * (size_t)S * n_window + (size_t)MSD_AP_NWT_MAX * (MSD_SOA_THREADS / 32) + MSD_SOA_THREADS + 32 + 8);
     if (smem + 64 > (size_t)ctx->max_smem_optin) return amofb_fail(ctx, AMOFB_ERR_ARG, "%d frames and %d window lengths do not fit the shared-memory series buffer", p->T, n_window);
+    // the autocorrelation form runs in the wide-tile kernel (two series buffers) whenever they fit; shape: the smallest
+    // instantiated number of sums per thread covering the request (or 32 per pass), and the frames per tile that waste the fewest slots
+    int wide_kb = 0, wide_nwt = 0, wide_rowcap = 0;
+    size_t wide_smem = 0;
+    if (!env_int("AMOFB_MSD_NO_WIDE", 0)) {
+        wide_nwt = n_window <= 13 ? 13 : n_window <= 25 ? 25 : 32;
+        if (int f = env_int("AMOFB_MSD_WIDE_NWT", 0)) wide_nwt = f == 13 || f == 25 ? f : 32;
+        double best = -1.0;
+        for (int kb : {6, 8, 10}) {
+            if (int f = env_int("AMOFB_MSD_WIDE_KB", 0)) if (kb != f) continue;
+            const long long span = (long long)kb * ap_delta, nsr = (p->T - 2 + span) / span, ntask = nsr * ap_delta;
+            const long long rounds = (ntask + MSD_WIDE_THREADS - 1) / MSD_WIDE_THREADS;
+            const double fill = (double)(p->T - 1) / (double)(rounds * MSD_WIDE_THREADS * kb);
+            const double ppl = (double)(kb * (wide_nwt - 1)) / (double)(kb + wide_nwt - 1);              // products per shared-memory read
+            const double eff = fill * std::min(1.0, ppl / 6.0);
+            if (eff > best + 1e-9) { best = eff; wide_kb = kb; wide_rowcap = (int)((std::max<long long>(p->Tp, nsr * span + 1) + 1) & ~1LL); }
+        }
+        wide_smem = sizeof(double) * (2 * (size_t)wide_rowcap + 2 * (size_t)S * n_window + (size_t)wide_nwt * (MSD_WIDE_THREADS / 32) + MSD_WIDE_THREADS + 8);
+        if (!wide_kb || wide_smem + 64 > (size_t)ctx->max_smem_optin) wide_kb = 0;
+    }
     for (int form = env_int("AMOFB_MSD_NO_DOT", 0) ? 1 : 0; form < 2; ++form) {
         const bool dot = form == 0;
+        const bool wide = dot && wide_kb > 0;
         const void *kfn = nullptr;
+        if (wide) {
+#define AMOFB_WIDE_KERNEL(KB_) (wide_nwt == 13 ? (const void *)k_msd_window_wide<KB_, 13> : wide_nwt == 25 ? (const void *)k_msd_window_wide<KB_, 25> \
+                                               : (const void *)k_msd_window_wide<KB_, 32>)
+            kfn = wide_kb == 6 ? AMOFB_WIDE_KERNEL(6) : wide_kb == 8 ? AMOFB_WIDE_KERNEL(8) : AMOFB_WIDE_KERNEL(10);
+#undef AMOFB_WIDE_KERNEL
+            if (env_int("AMOFB_MSD_DEBUG", 0)) fprintf(stderr, "[amofb msd] wide window kernel: %d frames x %d sums per tile, %d doubles per series buffer, %zu bytes of shared memory\n", wide_kb, wide_nwt, wide_rowcap, wide_smem);
+        } else {
 #define AMOFB_SOA_KERNEL(NWT_) (dot ? (const void *)k_msd_window_soa<MSD_SOA_KB, NWT_, true> : (const void *)k_msd_window_soa<MSD_SOA_KB, NWT_, false>)
         switch (ap_nwt) {
             case 5: kfn = AMOFB_SOA_KERNEL(5); break;
@@ -551,9 +581,11 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
             default: kfn = AMOFB_SOA_KERNEL(13); ap_nwt = 13; break;
         }
 #undef AMOFB_SOA_KERNEL
+        }
+        const size_t smem_use = wide ? wide_smem : smem;
         int per_sm = 0;
-        CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_use));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem_use));
         if (per_sm < 1) return amofb_fail(ctx, AMOFB_ERR_CUDA, "window kernel does not fit on an SM");
         const int grid = std::max(1, std::min(p->n, ctx->num_sms * per_sm));
         double *d_partial = nullptr;
@@ -579,12 +611,45 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
         const double *a_P = p->d_P; const uint8_t *a_sp = p->d_species; const int *a_perm = d_perm;
         int a_n = p->n, a_T = p->T, a_tp = p->Tp, a_S = S, a_nw = n_window, a_delta = ap_delta;
         void *kargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_perm, (void *)&a_n, (void *)&a_T, (void *)&a_tp, (void *)&a_delta, (void *)&a_nw, (void *)&ap_ng, (void *)&a_S, (void *)&d_partial};
-        cudaError_t e = cudaLaunchKernel(kfn, dim3(grid), dim3(threads), kargs, smem, ctx->s_compute);
+        int *d_pieces = nullptr;
+        if (wide) {
+            // ranges of frames for the sums of squares, per pass: cut at m + 1 and T - m for every window length m of the pass, then
+            // into pieces of at most c frames, with the smallest c that leaves no more pieces than threads
+            const int npass = (n_window + wide_nwt - 1) / wide_nwt;
+            std::vector<int> pieces((size_t)npass * (threads + 1));
+            for (int ps = 0; ps < npass; ++ps) {
+                std::vector<int> cut = {1, p->T};
+                for (int w = ps * wide_nwt; w < std::min(n_window, (ps + 1) * wide_nwt); ++w) {
+                    const long long m = (long long)w * ap_delta;
+                    if (m + 1 > 1 && m + 1 < p->T) cut.push_back((int)(m + 1));
+                    if (p->T - m > 1 && p->T - m < p->T) cut.push_back((int)(p->T - m));
+                }
+                std::sort(cut.begin(), cut.end());
+                cut.erase(std::unique(cut.begin(), cut.end()), cut.end());
+                int c = std::max(1, (p->T + threads - 1) / threads);
+                for (;; ++c) {
+                    long long np = 0;
+                    for (size_t i = 0; i + 1 < cut.size(); ++i) np += (cut[i + 1] - cut[i] + c - 1) / c;
+                    if (np <= threads) break;
+                }
+                int *out = pieces.data() + (size_t)ps * (threads + 1);
+                int at = 0;
+                for (size_t i = 0; i + 1 < cut.size(); ++i)
+                    for (int k = cut[i]; k < cut[i + 1]; k += c) out[at++] = k;
+                for (; at <= threads; ++at) out[at] = p->T;
+            }
+            if (int rc2 = dev_alloc(ctx, &d_pieces, pieces.size())) { pool_put(ctx, d_partial); pool_put(ctx, d_perm); return rc2; }
+            cudaMemcpy(d_pieces, pieces.data(), sizeof(int) * pieces.size(), cudaMemcpyHostToDevice);
+        }
+        const int *a_pieces = d_pieces;
+        void *wargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_perm, (void *)&a_pieces, (void *)&a_n, (void *)&a_T, (void *)&a_tp, (void *)&a_delta, (void *)&a_nw, (void *)&a_S, (void *)&wide_rowcap, (void *)&d_partial};
+        cudaError_t e = cudaLaunchKernel(kfn, dim3(grid), dim3(threads), wide ? wargs : kargs, smem_use, ctx->s_compute);
         ctx->launches += 1;
         if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, ctx->s_compute);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
         pool_put(ctx, d_partial);
         pool_put(ctx, d_perm);
+        pool_put(ctx, d_pieces);
         CUDA_TRY(ctx, e);
         bool redo = false;
         for (int i = 0; i < S * n_window; ++i) {

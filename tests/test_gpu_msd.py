@@ -238,6 +238,30 @@ def test_streaming_path_matches_oracle(backend, seed, T, n, tri, fixed, slab, de
     np.testing.assert_allclose(com, (masses[None, :, None] * pos).sum(axis=1) / masses.sum(), rtol=1e-13, atol=1e-13)
 
 
+@pytest.mark.parametrize("T,n,delta,kb,nwt", [
+    (1201, 37, 25, 6, 0),        # odd T, 24 window lengths -> 25 sums per thread
+    (1200, 20, 290, 8, 0),       # a stride beyond the block size: 3 window lengths
+    (1000, 64, 20, 10, 13),      # 25 window lengths forced into two passes of 13
+    (640, 30, 4, 8, 0),          # 80 window lengths: three passes of 32, later passes start at a window offset
+    (333, 9, 1, 10, 32),         # stride 1, 166 window lengths
+])
+def test_wide_window_kernel_shapes(backend, monkeypatch, T, n, delta, kb, nwt):
+    """k_msd_window_wide (two series buffers, all windows of a pass in one register tile) against the oracle AND against the
+    narrow kernel it replaced, for every tile height and for requests of one and of several passes."""
+    S = 2
+    pos, cells, spec, masses = _walk(900 + T, T, n, True, nspec=S)
+    window = np.arange(0, T // 2, delta)
+    monkeypatch.setenv("AMOFB_MSD_WIDE_KB", str(kb))
+    if nwt:
+        monkeypatch.setenv("AMOFB_MSD_WIDE_NWT", str(nwt))
+    wide, _ = _gpu_stream(backend, pos, cells, spec, masses, S, window, 96)
+    monkeypatch.setenv("AMOFB_MSD_NO_WIDE", "1")
+    narrow, _ = _gpu_stream(backend, pos, cells, spec, masses, S, window, 96)
+    want, _ = orc.msd_window(pos, cells, masses, spec, S, window)
+    np.testing.assert_allclose(wide, want, rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(narrow, want, rtol=RTOL, atol=1e-13)
+
+
 def test_streaming_forms_agree_and_fall_back(backend, monkeypatch):
     """The autocorrelation form must agree with the difference form, and a request whose windows are small against the
     squares they are taken from (ballistic drift, lag 1) must come out right all the same (the library re-runs it in the
