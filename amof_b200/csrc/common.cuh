@@ -245,6 +245,19 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, uns
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+// the same with a suspend-time hint: the warp sleeps in the barrier unit (up to ~ns nanoseconds per attempt) instead of spinning
+// through the issue slots of the warps that have work
+__device__ __forceinline__ void mbar_wait_hint(unsigned mbar, unsigned parity, unsigned ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAITH_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra MBAR_DONEH_%=;\n"
+        "bra MBAR_WAITH_%=;\n"
+        "MBAR_DONEH_%=:\n"
+        "}\n" :: "r"(mbar), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
     asm volatile(
         "{\n"

@@ -693,6 +693,94 @@ __global__ void __launch_bounds__(COMMIT_THREADS, 3) k_msd_slab_commit(const dou
     }
 }
 
+// Register version (round 2; ncu of the kernel above: 7 barriers per round, the serial scan -- half of the block idle -- holds
+// 37 % of the stall samples, 3.2 TB/s).  A lane owns one (atom, component) COLUMN for the whole slab: previous position and
+// running sum stay in registers.  A warp holds 10 atoms (30 lanes: the three components of an atom are neighbouring lanes, so
+// the wrap's 3x3 products take the other components by shuffle; 2 lanes idle), a block 12 warps = 120 atoms.  Per round of
+// REGF frames: REGF independent loads per lane (240-byte runs per warp and frame, the warps of a block back to back), then
+// shift -> difference -> wrap -> running sum in registers, the sums into a padded tile, ONE barrier, and the transposed
+// write-out (half a warp per column: 128-byte runs of the atom-major store).  Two tiles alternate, so the write-out of a round
+// overlaps the loads of the next.  Expressions and order are those of wrap_disp / wrap_disp_diag: the same bits.
+#define REGF 16
+#define REG_THREADS 384
+#define REG_ATOMS (10 * (REG_THREADS / 32))
+#define REG_COLS (3 * REG_ATOMS)
+#define REG_LD (REG_COLS + 1)
+#define REG_COM_MAX 256                   // frames per host slab (stage_frames is at most 256); longer device slabs take the kernel above
+#define REG_SMEM (sizeof(double) * (2 * REGF * REG_LD + 3 * REG_COM_MAX))
+template <int CELL>      // 0 = one cell per frame, 1 = the same cell in every frame, 2 = the same orthorhombic cell
+__global__ void __launch_bounds__(REG_THREADS, 2) k_msd_slab_commit_reg(const double *__restrict__ slab, double *__restrict__ P,
+                                                                        const MsdGeom *__restrict__ geom, const double *__restrict__ com,
+                                                                        double *__restrict__ carry, int n, int Tp, int first, int count) {
+    extern __shared__ __align__(16) double reg_sm[];
+    double *s_com = reg_sm + 2 * REGF * REG_LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a0 = blockIdx.x * REG_ATOMS, na = min(REG_ATOMS, n - a0), ncol = 3 * na;
+    const int comp = lane % 3, base = lane - comp;            // lanes 30, 31: comp 0 / 1 of a phantom atom, never `mine`
+    const int col = 30 * warp + lane;
+    const bool mine = lane < 30 && col < ncol;
+    const size_t cat = (size_t)(a0 + col / 3) * 6 + (size_t)comp;
+    double prev = (mine && first > 0) ? carry[cat] : 0.0, run = (mine && first > 0) ? carry[cat + 3] : 0.0;
+    const double shift = (0.0 - 0.5) - 1e-7;
+    double i0 = 0.0, i1 = 0.0, i2 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;     // inverse column `comp`, cell column `comp`
+    if (CELL != 0) {
+        i0 = geom[0].inv[comp]; i1 = geom[0].inv[3 + comp]; i2 = geom[0].inv[6 + comp];
+        c0 = geom[0].cell[comp]; c1 = geom[0].cell[3 + comp]; c2 = geom[0].cell[6 + comp];
+    }
+    for (int i = tid; i < 3 * count; i += REG_THREADS) s_com[i] = com[i];
+    __syncthreads();
+    const double *src = slab + (size_t)a0 * 3 + col;
+    const size_t fstride = (size_t)n * 3;
+    int buf = 0;
+    for (int k0 = 0; k0 < count; k0 += REGF, buf ^= 1) {
+        const int nr = min(REGF, count - k0);
+        double *tile = reg_sm + (size_t)buf * REGF * REG_LD;
+        double v[REGF];
+#pragma unroll
+        for (int r = 0; r < REGF; ++r) v[r] = (mine && r < nr) ? src[(size_t)(k0 + r) * fstride] : 0.0;
+#pragma unroll
+        for (int r = 0; r < REGF; ++r) {
+            if (r < nr) {                                       // uniform over the block: the shuffles below are convergent
+                const int k = first + k0 + r;
+                const double x = v[r] - s_com[3 * (k0 + r) + comp];      // translate(-cg), msd.py:237
+                const double e = x - prev;
+                prev = x;
+                if (k > 0) {                                    // delta_0 = 0: the running sum is taken relative to the first frame
+                    double d;
+                    const double ex = __shfl_sync(0xffffffffu, e, base), ey = __shfl_sync(0xffffffffu, e, base + 1),
+                                 ez = __shfl_sync(0xffffffffu, e, min(base + 2, 31));
+                    if (CELL == 0) {
+                        const MsdGeom &G = geom[k - 1];         // cell of frame k-1 wraps k-1 -> k
+                        i0 = G.inv[comp]; i1 = G.inv[3 + comp]; i2 = G.inv[6 + comp];
+                        c0 = G.cell[comp]; c1 = G.cell[3 + comp]; c2 = G.cell[6 + comp];
+                    }
+                    double g;
+                    if (CELL == 2) g = np_mod1(e * (comp == 0 ? i0 : comp == 1 ? i1 : i2) - shift) + shift;      // wrap_disp_diag: the diagonal entry
+                    else g = np_mod1(((ex * i0 + ey * i1) + ez * i2) - shift) + shift;
+                    if (CELL == 2) d = g * (comp == 0 ? c0 : comp == 1 ? c1 : c2);
+                    else {
+                        const double g0 = __shfl_sync(0xffffffffu, g, base), g1 = __shfl_sync(0xffffffffu, g, base + 1),
+                                     g2 = __shfl_sync(0xffffffffu, g, min(base + 2, 31));
+                        d = (g0 * c0 + g1 * c1) + g2 * c2;
+                    }
+                    run += d;
+                }
+                if (mine) tile[r * REG_LD + col] = run;
+            }
+        }
+        __syncthreads();        // the tile is complete; the other tile's write-out (previous round) was finished by everyone who got here
+        {
+            const int f = lane & 15, half = lane >> 4;
+            if (f < nr) {
+                double *dst = P + (size_t)a0 * 3 * Tp + (size_t)(first + k0 + f);
+                for (int cc = 2 * warp + half; cc < ncol; cc += 2 * (REG_THREADS / 32)) dst[(size_t)cc * Tp] = tile[f * REG_LD + cc];
+            }
+        }
+        // no second barrier: the next round fills the OTHER tile, and the round after that passes the barrier above first
+    }
+    if (mine) { carry[cat] = prev; carry[cat + 3] = run; }
+}
+
 // One component of one atom at a time: |R_k - R_j|^2 and R_k . R_j are sums over x, y, z, so the block stages 8*Tp bytes
 // instead of 24*Tp, several blocks share an SM, and one block's bulk copy and barriers hide behind the others' tiles.
 #ifndef MSD_SOA_THREADS
@@ -742,25 +830,50 @@ __device__ __forceinline__ void msd_soa_tile(const double *__restrict__ sm, int 
 //     body, the others stop at the first partner before frame 1 (frame 0 is the origin: exactly zero);
 //   * two series buffers: the bulk copy of the next component is in flight while this one is worked on, and a block never
 //     waits at a barrier for data.
-__device__ __forceinline__ double msd_lds(unsigned addr) {
+#ifndef MSD_WIDE_PLAIN_LDS
+#define MSD_WIDE_PLAIN_LDS 1        // 1: ordinary loads the compiler may schedule early; 0: ld.shared through a 32-bit address, kept in order
+#endif
+__device__ __forceinline__ double msd_lds(unsigned addr, const char *ptr) {
+#if MSD_WIDE_PLAIN_LDS
+    return *reinterpret_cast<const double *>(ptr);
+#else
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
+#endif
 }
 
-// sb: shared byte address of frame b of the series; d8 = 8 delta; lag8 = 8 wlo delta; partner slot v is frame b + (v - wlo) delta
-// and exists iff v >= -e (e = s KB - wlo)
-template <int KB, int NWT, bool WLO0, bool FULL>
-__device__ __forceinline__ void msd_wide_tile(unsigned sb, int d8, int lag8, int e, double (&acc)[NWT]) {
+// sb / sp: shared byte address of / pointer to frame b of the series; d8 = 8 delta; lag8 = 8 wlo delta; partner slot v is frame
+// b + (v - wlo) delta and exists iff v >= -e (e = s KB - wlo)
+#ifndef MSD_WIDE_AHEAD
+#define MSD_WIDE_AHEAD 3            // partner reads issued this many slots before their products
+#endif
+// EC >= 0: the tile's e is the compile-time EC (no tests in the body); EC < 0: e is only known at run time
+template <int KB, int NWT, bool WLO0, int EC>
+__device__ __forceinline__ void msd_wide_tile(unsigned sb, const char *sp, int d8, int lag8, int e_rt, double (&acc)[NWT]) {
+    constexpr bool RT = EC < 0;
+    const int e = RT ? e_rt : EC;
     double kv[KB];
 #pragma unroll
-    for (int i = 0; i < KB; ++i) kv[i] = msd_lds(sb + (unsigned)(i * d8));
+    for (int i = 0; i < KB; ++i) kv[i] = msd_lds(sb + (unsigned)(i * d8), sp + i * d8);
+    constexpr int V0 = WLO0 ? -1 : KB - 1;                  // first partner slot that is read from shared memory
+    double ring[MSD_WIDE_AHEAD];
+#pragma unroll
+    for (int a = 0; a < MSD_WIDE_AHEAD; ++a) {
+        const int v = V0 - a;
+        ring[a] = (v > -NWT && v >= -e) ? msd_lds(sb + (unsigned)(v * d8 - lag8), sp + (v * d8 - lag8)) : 0.0;
+    }
 #pragma unroll
     for (int v = KB - 1; v > -NWT; --v) {
-        if (!FULL && (!WLO0 || v < 0) && v < -e) break;
+        if ((!WLO0 || v < 0) && v < -e) break;
         double pv;
         if (WLO0 && v >= 0) pv = kv[v];
-        else pv = msd_lds(sb + (unsigned)(v * d8 - lag8));
+        else {
+            const int slot = (V0 - v) % MSD_WIDE_AHEAD;    // compile-time after unrolling
+            pv = ring[slot];
+            const int vn = v - MSD_WIDE_AHEAD;
+            ring[slot] = (vn > -NWT && vn >= -e) ? msd_lds(sb + (unsigned)(vn * d8 - lag8), sp + (vn * d8 - lag8)) : 0.0;
+        }
 #pragma unroll
         for (int i = 0; i < KB; ++i) {
             const int t = i - v;
@@ -769,38 +882,54 @@ __device__ __forceinline__ void msd_wide_tile(unsigned sb, int d8, int lag8, int
     }
 }
 
-#define MSD_WIDE_THREADS 256
+// first pass (windows from 0): e = s KB is one of a few values below NWT - 1, each with its own test-free body
+template <int KB, int NWT, int LVL>
+__device__ __forceinline__ void msd_wide_first(int s, unsigned sb, const char *sp, int d8, double (&acc)[NWT]) {
+    if constexpr (LVL * KB >= NWT - 1) {
+        msd_wide_tile<KB, NWT, true, NWT - 1>(sb, sp, d8, 0, 0, acc);
+    } else {
+        if (s == LVL) msd_wide_tile<KB, NWT, true, LVL * KB>(sb, sp, d8, 0, 0, acc);
+        else msd_wide_first<KB, NWT, LVL + 1>(s, sb, sp, d8, acc);
+    }
+}
+
+#define MSD_WIDE_THREADS 512
+#ifndef MSD_WIDE_WAIT_NS
+#define MSD_WIDE_WAIT_NS 4000       // suspend-time hint of the series wait (0: plain try_wait spin)
+#endif
 #define MSD_WIDE_NWT_MAX 32
+#define MSD_WIDE_MAX_BUF 4
 
 // partial[block][2][S][nw] as k_msd_window_soa<.., true>: [0] sum of R_k . R_{k-m}, [1] sum of |R_k|^2 + |R_{k-m}|^2.
-// rowcap: doubles per series buffer (tp + the zero tail, even).  pieces[pass][threads + 1]: frame ranges for the sums of squares
-// of a pass -- thread t adds up the frames [pieces[t], pieces[t+1]) of every series; no range straddles m + 1 or T - m for a
-// window length m of the pass, so  sum_{k=m+1}^{T-1} v_k^2 + sum_{j=1}^{T-1-m} v_j^2  is a sum of whole ranges.
-// Dynamic shared memory: 2 rowcap | 2 S nw | nwarp NWT | threads.
+// rowcap: doubles per series buffer (tp + the zero tail, even); nbuf series buffers (2 .. MSD_WIDE_MAX_BUF).
+// pieces[pass][threads + 1]: frame ranges for the sums of squares of a pass -- thread t adds up the frames [pieces[t], pieces[t+1]) of
+// every series; no range straddles m + 1 or T - m for a window length m of the pass, so
+// sum_{k=m+1}^{T-1} v_k^2 + sum_{j=1}^{T-1-m} v_j^2  is a sum of whole ranges.
+// Dynamic shared memory: nbuf rowcap | 2 S nw | nwarp NWT | threads.
 //
-// No block-wide barrier in the steady state: a warp waits for a series on the buffer's mbarrier, works through its tiles, and
-// counts itself out of the buffer; the last warp out issues the bulk copy of the series after next into it.  Warps drift up to
-// one series apart, and the thread -> task map is mirrored on odd series, so that a thread with the short (early-frame) tiles on
-// one series has the long ones on the next: the per-series imbalance (tiles near frame 0 have few partners) evens out.
-template <int KB, int NWT>
-__global__ void __launch_bounds__(MSD_WIDE_THREADS, 2) k_msd_window_wide(const double *__restrict__ P, const uint8_t *__restrict__ species,
+// One block per SM and no block-wide barrier in the steady state: a warp waits for a series on its buffer's mbarrier, works
+// through its tiles and counts itself out of the buffer; the last warp out issues the bulk copy of the series nbuf further on.
+// Warps drift up to nbuf - 1 series apart.  The tiles of a series are not equally long (those near frame 0 have few partners), so
+// the thread -> tile map moves on by one super-row with every series: over nsr series every thread has had every length.
+template <int KB, int NWT, int THREADS>
+__global__ void __launch_bounds__(THREADS, MSD_WIDE_THREADS / THREADS) k_msd_window_wide(const double *__restrict__ P, const uint8_t *__restrict__ species,
                                                                          const int *__restrict__ perm, const int *__restrict__ pieces,
-                                                                         int n, int T, int tp, int delta, int nw, int S, int rowcap,
+                                                                         int n, int T, int tp, int delta, int nw, int S, int rowcap, int nbuf,
                                                                          double *__restrict__ partial) {
     extern __shared__ __align__(16) double sm[];
-    double *s_acc = sm + 2 * (size_t)rowcap;                // [S][nw]
+    double *s_acc = sm + (size_t)nbuf * rowcap;             // [S][nw]
     double *s_ss = s_acc + (size_t)S * nw;                  // [S][nw]
     double *s_red = s_ss + (size_t)S * nw;                  // [nwarp][NWT]
-    double *s_part = s_red + (size_t)NWT * (MSD_WIDE_THREADS / 32);      // [threads]: sums of squares per range
-    __shared__ __align__(8) unsigned long long s_mbar[2];
-    __shared__ unsigned s_done[2];
+    double *s_part = s_red + (size_t)NWT * (THREADS / 32);      // [threads]: sums of squares per range
+    __shared__ __align__(8) unsigned long long s_mbar[MSD_WIDE_MAX_BUF];
+    __shared__ unsigned s_done[MSD_WIDE_MAX_BUF];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 2 * S * nw; i += blockDim.x) s_acc[i] = 0.0;      // s_acc and s_ss are adjacent
-    for (int b = 0; b < 2; ++b)                                                     // the zero tails (never written again)
+    for (int b = 0; b < nbuf; ++b)                                                  // the zero tails (never written again)
         for (int i = tp + threadIdx.x; i < rowcap; i += blockDim.x) sm[(size_t)b * rowcap + i] = 0.0;
     const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&s_mbar[0]);
     const unsigned sm_addr = (unsigned)__cvta_generic_to_shared(sm);
-    if (threadIdx.x == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); s_done[0] = 0u; s_done[1] = 0u; }
+    if ((int)threadIdx.x < nbuf) { mbar_init(mbar0 + 8u * threadIdx.x, 1); s_done[threadIdx.x] = 0u; }
     __syncthreads();
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int a_lo = min(n, blockIdx.x * per), a_hi = min(n, a_lo + per);
@@ -810,16 +939,13 @@ __global__ void __launch_bounds__(MSD_WIDE_THREADS, 2) k_msd_window_wide(const d
     const int ntask = nsr * delta;
     const unsigned row_bytes = 8u * (unsigned)tp;
     const int d8 = 8 * delta;
-    // this thread's tasks q = q0, q0 + blockDim, ...: (super-row s, residue r), stepped without a division; q0 = tid on even
-    // series and blockDim - 1 - tid on odd ones
-    const int qe = (int)threadIdx.x, qo = (int)blockDim.x - 1 - (int)threadIdx.x;
-    const int se_first = qe / delta, re_first = qe - se_first * delta;
-    const int so_first = qo / delta, ro_first = qo - so_first * delta;
+    // this thread's tiles on series 0: q = tid, tid + blockDim, ...: (super-row s, residue r), stepped without a division
+    const int s_first = (int)threadIdx.x / delta, r_first = (int)threadIdx.x - s_first * delta;
     const int s_step = (int)blockDim.x / delta, r_step = (int)blockDim.x - s_step * delta;
-    auto issue = [&](int row) {                             // one thread: bulk copy of series `row` of the block into buffer row & 1
+    auto issue = [&](int row, int b) {                      // one thread: bulk copy of series `row` of the block into buffer b
         const int a = perm[a_lo + row / 3];
         const char *src = reinterpret_cast<const char *>(P + ((size_t)a * 3 + (size_t)(row % 3)) * tp);
-        const unsigned dst = sm_addr + (unsigned)(row & 1) * 8u * (unsigned)rowcap, mb = mbar0 + 8u * (unsigned)(row & 1);
+        const unsigned dst = sm_addr + (unsigned)b * 8u * (unsigned)rowcap, mb = mbar0 + 8u * (unsigned)b;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(mb, row_bytes);
         for (unsigned o = 0; o < row_bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, row_bytes - o), mb);
@@ -832,10 +958,9 @@ __global__ void __launch_bounds__(MSD_WIDE_THREADS, 2) k_msd_window_wide(const d
         for (int w = 0; w < NWT; ++w) acc[w] = 0.0;
         double sq = 0.0;
         int cur_sp = -1;
-        if (threadIdx.x == 0) {                             // both buffers are free: the previous pass ended with a barrier
-            if (nrow > 0) issue(0);
-            if (nrow > 1) issue(1);
-        }
+        if ((int)threadIdx.x < nbuf && (int)threadIdx.x < nrow) issue(threadIdx.x, threadIdx.x);   // all buffers are free: the previous pass ended with a barrier
+        int b = 0, gen = 0;                                 // buffer of the series, and how many series of this pass it has held before
+        int rot = 0;                                        // super-rows the tile map has moved on (series index modulo nsr)
         for (int row = 0; row <= nrow; ++row) {
             if (row % 3 == 0) {
                 // the block's atoms are visited in species order (perm: a stable sort of [a_lo, a_hi) by species), so the register
@@ -879,42 +1004,51 @@ __global__ void __launch_bounds__(MSD_WIDE_THREADS, 2) k_msd_window_wide(const d
                 }
             }
             if (row >= nrow) break;
-            const int b = row & 1;
-            {   // completed phases of buffer b before this series: those of this pass with its parity, plus all of the earlier passes
-                const int before = (row >> 1) + pass * ((nrow + 1 - b) >> 1);
+            {   // completed phases of buffer b before this series: those of this pass, plus all of the earlier passes
+                const int before = gen + pass * ((nrow - b + nbuf - 1) / nbuf);
+#if MSD_WIDE_WAIT_NS > 0
+                mbar_wait_hint(mbar0 + 8u * (unsigned)b, (unsigned)(before & 1), MSD_WIDE_WAIT_NS);
+#else
                 mbar_wait(mbar0 + 8u * (unsigned)b, (unsigned)(before & 1));
+#endif
             }
             const unsigned xb = sm_addr + (unsigned)b * 8u * (unsigned)rowcap;
             const double *x = sm + (size_t)b * rowcap;
-            for (int k = pk0; k < pk1; ++k) sq = __fma_rn(x[k], x[k], sq);
-            int sq_ = b ? so_first : se_first, r = b ? ro_first : re_first;
-            for (int q = b ? qo : qe; q < ntask; q += blockDim.x) {
-                const int e = sq_ * KB - w0;
-                const unsigned sb = xb + 8u * (unsigned)(1 + sq_ * span + r);
-                if (e > -KB) {
-                    // a warp whose lanes are not all in the unchecked case runs the checked body for all of them (one code path)
-                    const bool full = __all_sync(__activemask(), e >= NWT - 1);
-                    if (full) {
-                        if (w0 == 0) msd_wide_tile<KB, NWT, true, true>(sb, d8, lag8, e, acc);
-                        else msd_wide_tile<KB, NWT, false, true>(sb, d8, lag8, e, acc);
-                    } else {
-                        if (w0 == 0) msd_wide_tile<KB, NWT, true, false>(sb, d8, lag8, e, acc);
-                        else msd_wide_tile<KB, NWT, false, false>(sb, d8, lag8, e, acc);
-                    }
+            {   // four partial sums: one chain of dependent FMAs would cost its full latency per frame
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+                int k = pk0;
+                for (; k + 3 < pk1; k += 4) {
+                    q0 = __fma_rn(x[k], x[k], q0); q1 = __fma_rn(x[k + 1], x[k + 1], q1);
+                    q2 = __fma_rn(x[k + 2], x[k + 2], q2); q3 = __fma_rn(x[k + 3], x[k + 3], q3);
                 }
+                for (; k < pk1; ++k) q0 = __fma_rn(x[k], x[k], q0);
+                sq += (q0 + q1) + (q2 + q3);
+            }
+            int sq_ = s_first + rot, r = r_first;           // (s + rot) mod nsr: the wrap is applied per tile below
+            for (int q = threadIdx.x; q < ntask; q += blockDim.x) {
+                const int sw = sq_ >= nsr ? sq_ - nsr : sq_;
+                const int e = sw * KB - w0;
+                const int off = 8 * (1 + sw * span + r);
+                const unsigned sb = xb + (unsigned)off;
+                const char *sp = reinterpret_cast<const char *>(x) + off;
+                if (w0 == 0) msd_wide_first<KB, NWT, 0>(sw, sb, sp, d8, acc);
+                else if (e >= NWT - 1) msd_wide_tile<KB, NWT, false, NWT - 1>(sb, sp, d8, lag8, 0, acc);
+                else if (e > -KB) msd_wide_tile<KB, NWT, false, -1>(sb, sp, d8, lag8, e, acc);
                 sq_ += s_step; r += r_step;
                 if (r >= delta) { r -= delta; ++sq_; }
             }
-            // this warp has left buffer b; the last warp out refills it with the series after next
+            // this warp has left buffer b; the last warp out refills it with the series nbuf further on
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
                 if (atomicAdd(&s_done[b], 1u) == (unsigned)(nwarp - 1)) {
                     s_done[b] = 0u;
                     __threadfence_block();
-                    if (row + 2 < nrow) issue(row + 2);
+                    if (row + nbuf < nrow) issue(row + nbuf, b);
                 }
             }
+            if (++b == nbuf) { b = 0; ++gen; }
+            if (++rot == nsr) rot = 0;
         }
         __syncthreads();
     }

@@ -488,15 +488,21 @@ extern "C" int amofb_msd_slab_commit(amofb_ctx *ctx, const double *com) {
     const int first = q.first, count = q.count;
     double *d_com = p->d_com + 3 * (size_t)first;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, ctx->s_compute));   // pageable: staged before return
-    const int blocks = (p->n + COMMIT_A - 1) / COMMIT_A;
     const int cm = p->diag_cell ? 2 : (p->fixed_cell ? 1 : 0);
-    const void *kfn = cm == 2 ? (const void *)k_msd_slab_commit<2> : cm == 1 ? (const void *)k_msd_slab_commit<1> : (const void *)k_msd_slab_commit<0>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COMMIT_SMEM));
     {
         const double *a_slab = q.ptr; double *a_P = p->d_P; const MsdGeom *a_geom = p->d_geom; const double *a_com = d_com; double *a_carry = p->d_carry;
         int a_n = p->n, a_tp = p->Tp, a_first = first, a_count = count;
         void *kargs[] = {(void *)&a_slab, (void *)&a_P, (void *)&a_geom, (void *)&a_com, (void *)&a_carry, (void *)&a_n, (void *)&a_tp, (void *)&a_first, (void *)&a_count};
-        CUDA_TRY(ctx, cudaLaunchKernel(kfn, dim3(blocks), dim3(COMMIT_THREADS), kargs, COMMIT_SMEM, ctx->s_compute));
+        if (count <= REG_COM_MAX && !env_int("AMOFB_MSD_NO_COLUMN_COMMIT", 0)) {
+            // a lane per (atom, component) column, carry in registers, one barrier per round
+            const void *kfn = cm == 2 ? (const void *)k_msd_slab_commit_reg<2> : cm == 1 ? (const void *)k_msd_slab_commit_reg<1> : (const void *)k_msd_slab_commit_reg<0>;
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REG_SMEM));
+            CUDA_TRY(ctx, cudaLaunchKernel(kfn, dim3((p->n + REG_ATOMS - 1) / REG_ATOMS), dim3(REG_THREADS), kargs, REG_SMEM, ctx->s_compute));
+        } else {
+            const void *kfn = cm == 2 ? (const void *)k_msd_slab_commit<2> : cm == 1 ? (const void *)k_msd_slab_commit<1> : (const void *)k_msd_slab_commit<0>;
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COMMIT_SMEM));
+            CUDA_TRY(ctx, cudaLaunchKernel(kfn, dim3((p->n + COMMIT_A - 1) / COMMIT_A), dim3(COMMIT_THREADS), kargs, COMMIT_SMEM, ctx->s_compute));
+        }
     }
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
@@ -543,34 +549,48 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
     if (smem + 64 > (size_t)ctx->max_smem_optin) return amofb_fail(ctx, AMOFB_ERR_ARG, "%d frames and %d window lengths do not fit the shared-memory series buffer", p->T, n_window);
     // the autocorrelation form runs in the wide-tile kernel (two series buffers) whenever they fit; shape: the smallest
     // instantiated number of sums per thread covering the request (or 32 per pass), and the frames per tile that waste the fewest slots
-    int wide_kb = 0, wide_nwt = 0, wide_rowcap = 0;
+    int wide_kb = 0, wide_nwt = 0, wide_rowcap = 0, wide_nbuf = 0, wide_threads = 256;
     size_t wide_smem = 0;
     if (!env_int("AMOFB_MSD_NO_WIDE", 0)) {
         wide_nwt = n_window <= 13 ? 13 : n_window <= 25 ? 25 : 32;
         if (int f = env_int("AMOFB_MSD_WIDE_NWT", 0)) wide_nwt = f == 13 || f == 25 ? f : 32;
+        if (env_int("AMOFB_MSD_WIDE_THREADS", 0) == 512) wide_threads = 512;
         double best = -1.0;
         for (int kb : {6, 8, 10}) {
             if (int f = env_int("AMOFB_MSD_WIDE_KB", 0)) if (kb != f) continue;
             const long long span = (long long)kb * ap_delta, nsr = (p->T - 2 + span) / span, ntask = nsr * ap_delta;
-            const long long rounds = (ntask + MSD_WIDE_THREADS - 1) / MSD_WIDE_THREADS;
-            const double fill = (double)(p->T - 1) / (double)(rounds * MSD_WIDE_THREADS * kb);
+            const long long rounds = (ntask + wide_threads - 1) / wide_threads;
+            const double fill = (double)(p->T - 1) / (double)(rounds * wide_threads * kb);
             const double ppl = (double)(kb * (wide_nwt - 1)) / (double)(kb + wide_nwt - 1);              // products per shared-memory read
             const double eff = fill * std::min(1.0, ppl / 6.0);
             if (eff > best + 1e-9) { best = eff; wide_kb = kb; wide_rowcap = (int)((std::max<long long>(p->Tp, nsr * span + 1) + 1) & ~1LL); }
         }
-        wide_smem = sizeof(double) * (2 * (size_t)wide_rowcap + 2 * (size_t)S * n_window + (size_t)wide_nwt * (MSD_WIDE_THREADS / 32) + MSD_WIDE_THREADS + 8);
-        if (!wide_kb || wide_smem + 64 > (size_t)ctx->max_smem_optin) wide_kb = 0;
+        // 512 threads: one block per SM; 256 threads: two, each with half of the shared memory
+        const size_t fixed = sizeof(double) * (2 * (size_t)S * n_window + (size_t)wide_nwt * (wide_threads / 32) + wide_threads + 8);
+        const size_t sm_total = (size_t)ctx->max_smem_optin + 1024;
+        const size_t per_block = wide_threads == 512 ? (size_t)ctx->max_smem_optin : sm_total / 2 - 1024;
+        const size_t room = per_block > fixed + 256 ? per_block - fixed - 256 : 0;
+        wide_nbuf = wide_kb ? (int)std::min<size_t>(MSD_WIDE_MAX_BUF, room / (sizeof(double) * (size_t)wide_rowcap)) : 0;
+        if (wide_nbuf < 2 && wide_threads == 256 && wide_kb) {          // two buffers do not fit twice: one block of 256 threads per SM
+            const size_t room1 = (size_t)ctx->max_smem_optin > fixed + 256 ? (size_t)ctx->max_smem_optin - fixed - 256 : 0;
+            wide_nbuf = (int)std::min<size_t>(MSD_WIDE_MAX_BUF, room1 / (sizeof(double) * (size_t)wide_rowcap));
+        }
+        if (int f = env_int("AMOFB_MSD_WIDE_NBUF", 0)) wide_nbuf = std::min(wide_nbuf, std::max(2, f));
+        if (wide_nbuf < 2) wide_kb = 0;                       // not even two series buffers: the narrow kernel stages one at a time
+        wide_smem = fixed + sizeof(double) * (size_t)wide_nbuf * wide_rowcap;
     }
     for (int form = env_int("AMOFB_MSD_NO_DOT", 0) ? 1 : 0; form < 2; ++form) {
         const bool dot = form == 0;
         const bool wide = dot && wide_kb > 0;
         const void *kfn = nullptr;
         if (wide) {
-#define AMOFB_WIDE_KERNEL(KB_) (wide_nwt == 13 ? (const void *)k_msd_window_wide<KB_, 13> : wide_nwt == 25 ? (const void *)k_msd_window_wide<KB_, 25> \
-                                               : (const void *)k_msd_window_wide<KB_, 32>)
+#define AMOFB_WIDE_KERNEL2(KB_, TH_) (wide_nwt == 13 ? (const void *)k_msd_window_wide<KB_, 13, TH_> : wide_nwt == 25 ? (const void *)k_msd_window_wide<KB_, 25, TH_> \
+                                                     : (const void *)k_msd_window_wide<KB_, 32, TH_>)
+#define AMOFB_WIDE_KERNEL(KB_) (wide_threads == 512 ? AMOFB_WIDE_KERNEL2(KB_, 512) : AMOFB_WIDE_KERNEL2(KB_, 256))
             kfn = wide_kb == 6 ? AMOFB_WIDE_KERNEL(6) : wide_kb == 8 ? AMOFB_WIDE_KERNEL(8) : AMOFB_WIDE_KERNEL(10);
+#undef AMOFB_WIDE_KERNEL2
 #undef AMOFB_WIDE_KERNEL
-            if (env_int("AMOFB_MSD_DEBUG", 0)) fprintf(stderr, "[amofb msd] wide window kernel: %d frames x %d sums per tile, %d doubles per series buffer, %zu bytes of shared memory\n", wide_kb, wide_nwt, wide_rowcap, wide_smem);
+            if (env_int("AMOFB_MSD_DEBUG", 0)) fprintf(stderr, "[amofb msd] wide window kernel: %d threads, %d frames x %d sums per tile, %d series buffers of %d doubles, %zu bytes of shared memory\n", wide_threads, wide_kb, wide_nwt, wide_nbuf, wide_rowcap, wide_smem);
         } else {
 #define AMOFB_SOA_KERNEL(NWT_) (dot ? (const void *)k_msd_window_soa<MSD_SOA_KB, NWT_, true> : (const void *)k_msd_window_soa<MSD_SOA_KB, NWT_, false>)
         switch (ap_nwt) {
@@ -583,6 +603,7 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
 #undef AMOFB_SOA_KERNEL
         }
         const size_t smem_use = wide ? wide_smem : smem;
+        if (wide) threads = wide_threads; else threads = MSD_SOA_THREADS;
         int per_sm = 0;
         CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_use));
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem_use));
@@ -626,8 +647,8 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
                 }
                 std::sort(cut.begin(), cut.end());
                 cut.erase(std::unique(cut.begin(), cut.end()), cut.end());
-                int c = std::max(1, (p->T + threads - 1) / threads);
-                for (;; ++c) {
+                int c = std::max(1, (p->T + threads - 1) / threads) | 1;      // odd: neighbouring threads read different banks
+                for (;; c += 2) {
                     long long np = 0;
                     for (size_t i = 0; i + 1 < cut.size(); ++i) np += (cut[i + 1] - cut[i] + c - 1) / c;
                     if (np <= threads) break;
@@ -642,7 +663,7 @@ static int msd_window_soa(amofb_ctx *ctx, MsdState *p, int n_window, int ap_delt
             cudaMemcpy(d_pieces, pieces.data(), sizeof(int) * pieces.size(), cudaMemcpyHostToDevice);
         }
         const int *a_pieces = d_pieces;
-        void *wargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_perm, (void *)&a_pieces, (void *)&a_n, (void *)&a_T, (void *)&a_tp, (void *)&a_delta, (void *)&a_nw, (void *)&a_S, (void *)&wide_rowcap, (void *)&d_partial};
+        void *wargs[] = {(void *)&a_P, (void *)&a_sp, (void *)&a_perm, (void *)&a_pieces, (void *)&a_n, (void *)&a_T, (void *)&a_tp, (void *)&a_delta, (void *)&a_nw, (void *)&a_S, (void *)&wide_rowcap, (void *)&wide_nbuf, (void *)&d_partial};
         cudaError_t e = cudaLaunchKernel(kfn, dim3(grid), dim3(threads), wide ? wargs : kargs, smem_use, ctx->s_compute);
         ctx->launches += 1;
         if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, ctx->s_compute);
