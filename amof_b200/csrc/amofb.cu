@@ -334,6 +334,11 @@ struct Batcher {
     uint8_t *d_species_keep = nullptr;   // optional species filter of the cell list (bond angles)
     int *d_keep_idx = nullptr;           // with the filter: original indices of the atoms that pass it
     int n_keep = 0;                      // atoms per frame that pass it (= n_atoms without a filter)
+    int *d_centre_rank = nullptr;        // optional (bond angles): rank of every kept atom among the possible centres of a frame, or -1
+    unsigned *d_centre_list = nullptr;   //   and the compact list the scatter kernel fills: [cap_frames * n_centres]
+    int n_centres = 0;
+    int n_lists = 1;                     // cell lists per frame (bond angles: one per kept species)
+    uint8_t list_of[AMOFB_MAX_SPECIES] = {0};
     bool want_orig = false;              // keep the original index of every sorted atom
     BatchSlot slot[2];
     int next = 0;
@@ -352,7 +357,8 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
         s = BatchSlot();
     }
     pool_put(ctx, b.d_species); pool_put(ctx, b.d_species_keep); pool_put(ctx, b.d_keep_idx);
-    b.d_species = nullptr; b.d_species_keep = nullptr; b.d_keep_idx = nullptr;
+    pool_put(ctx, b.d_centre_rank); pool_put(ctx, b.d_centre_list);
+    b.d_species = nullptr; b.d_species_keep = nullptr; b.d_keep_idx = nullptr; b.d_centre_rank = nullptr; b.d_centre_list = nullptr;
 }
 
 // n_work: atoms per frame that enter the cell list (< n_atoms under a species filter): the batch is sized by the work, the raw
@@ -369,7 +375,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
     cap = std::min<long long>(cap, (1ll << 30) / (24ll * std::max(n_atoms, 1)));
     b.cap_frames = (int)std::min<long long>(std::max<long long>(cap, 1), 8192);
     if (max_frames > 0 && b.cap_frames > max_frames) b.cap_frames = max_frames;
-    b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0) + 1;
+    b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0 * AMOFB_MAX_SPECIES) + 1;      // per list at most 4 cells per atom + 64 (host_fill_geom)
     AMOFB_TRY(dev_alloc(ctx, &b.d_species, (size_t)n_atoms));
     CUDA_TRY(ctx, cudaMemcpy(b.d_species, species, (size_t)n_atoms, cudaMemcpyHostToDevice));
     size_t na = (size_t)b.cap_frames * n_atoms;
@@ -395,12 +401,22 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
 }
 
 // species filter of the cell list: atoms whose species has keep[] == 0 never enter it
-static int batcher_set_filter(amofb_ctx *ctx, Batcher &b, const uint8_t *species, const uint8_t *keep) {
+// centre_mask (optional, [AMOFB_MAX_SPECIES]): species that can be the centre of an angle; the scatter kernel then also lists them
+static int batcher_set_filter(amofb_ctx *ctx, Batcher &b, const uint8_t *species, const uint8_t *keep, const unsigned long long *centre_mask = nullptr) {
     std::vector<int> idx;
     idx.reserve((size_t)b.n_atoms);
     for (int i = 0; i < b.n_atoms; ++i)
         if (keep[species[i]]) idx.push_back(i);
     b.n_keep = (int)idx.size();
+    if (centre_mask && !idx.empty()) {
+        std::vector<int> crank(idx.size());
+        int nc = 0;
+        for (size_t k = 0; k < idx.size(); ++k) crank[k] = centre_mask[species[idx[k]]] ? nc++ : -1;
+        b.n_centres = nc;
+        AMOFB_TRY(dev_alloc(ctx, &b.d_centre_rank, crank.size()));
+        CUDA_TRY(ctx, cudaMemcpy(b.d_centre_rank, crank.data(), sizeof(int) * crank.size(), cudaMemcpyHostToDevice));
+        AMOFB_TRY(dev_alloc(ctx, &b.d_centre_list, (size_t)std::max(nc, 1) * (size_t)b.cap_frames));
+    }
     AMOFB_TRY(dev_alloc(ctx, &b.d_species_keep, (size_t)AMOFB_MAX_SPECIES));
     CUDA_TRY(ctx, cudaMemcpy(b.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice));
     AMOFB_TRY(dev_alloc(ctx, &b.d_keep_idx, idx.size() + 1));
@@ -432,12 +448,12 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     int cs_off = 0;
     for (int f = 0; f < nf; ++f) {
         FrameGeom &g = s.h_geom[f];
-        if (!host_fill_geom(g, cell + 9 * (size_t)f, b.rcut, b.cell_div, b.n_keep, b.cell_widen))
+        if (!host_fill_geom(g, cell + 9 * (size_t)f, b.rcut, b.cell_div, std::max(1, b.n_keep / b.n_lists), b.cell_widen))
             return amofb_fail(ctx, AMOFB_ERR_GEOMETRY, "frame %lld: singular cell or cell far smaller than the cutoff %g",
                               (long long)(b.frames_seen + f), b.rcut);
         g.cs_off = cs_off;
         g.frame_id = (int)(b.frames_seen + f);
-        cs_off += g.ncell + 1;
+        cs_off += b.n_lists * g.ncell + 1;
         b.volume_sum += host_cell_volume(cell + 9 * (size_t)f);
     }
     const double *raw = pos;
@@ -462,6 +478,9 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.orig = s.d_orig;
     pa.wraps = s.d_wraps;
     pa.slot = nullptr;
+    pa.centre_rank = b.d_centre_rank; pa.centre_list = b.d_centre_list; pa.n_centres = b.n_centres;
+    pa.n_lists = b.n_lists;
+    memcpy(pa.list_of, b.list_of, sizeof pa.list_of);
     long long total = (long long)nf * (b.d_keep_idx ? b.n_keep : b.n_atoms);
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;

@@ -17,7 +17,10 @@
 // [-1, 1] as ase.geometry.get_angles does, and located in a table of thresholds on -x that the host bisected with its own
 // libm acos and the np.histogram edge rule (P7), so the bin is the one the CPU path takes, bit for bit.
 #pragma once
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 #include "prep.cuh"
+namespace cg = cooperative_groups;
 
 #define BAD_NB_MAX 64        // neighbours of any species kept per centre
 #define BAD_MAX_TRIPLES 64
@@ -54,6 +57,11 @@ struct BadArgs {
     int tthr_smem;                // the threshold table fits in shared memory
     int n_keep;                   // atoms per frame in the (species-filtered) cell list
     const unsigned long long *centre_mask;               // [AMOFB_MAX_SPECIES] triples whose A matches this species
+    const unsigned *centre_list;                         // optional [n_frames * n_centres]: frame * n_keep + sorted position of every possible centre
+    int n_centres;
+    int n_lists;                                         // cell lists per frame: one per kept species (1: a single list of all kept atoms)
+    uint8_t list_of[AMOFB_MAX_SPECIES];                  // species -> its list
+    uint16_t partner_mask[AMOFB_MAX_SPECIES];            // species with a positive cutoff to this one
     double r2search;
     float inv_dtheta_f;
     int n_atoms, n_frames, n_species, nkeys, n_triples, nbins;
@@ -73,7 +81,11 @@ __device__ __forceinline__ int bad_bin(double t, const double *__restrict__ tthr
 #define BAD_MIN_BLOCKS 8      // 64 registers
 #endif
 __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad_search(BadArgs a) {
-    const long long t_id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long t_id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (a.centre_list) {            // every lane is a possible centre (on a ZIF 'Zn-N' analysis one kept atom in five is)
+        if (t_id >= (long long)a.n_frames * a.n_centres) return;
+        t_id = (long long)a.centre_list[t_id];
+    }
     if (t_id >= (long long)a.n_frames * a.n_keep) return;
     const int f = (int)(t_id / a.n_keep);
     const int i = (int)(t_id - (long long)f * a.n_keep);
@@ -106,76 +118,87 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad_search(BadArgs a) {
         if (nz < 3) { zq[nz] = q2; zl[nz] = len; zs[nz] = s2; ++nz; } else many_wraps = true;
         d2 += len;
     }
-    // Two steps.  A) every lane lists its candidate ranges -- (row, z run) -> [first, end) | image code -- in shared memory,
-    // in lockstep (nine rows, one or two z runs each).  B) ONE flat loop over the candidates of all its ranges: a lane
-    // opens its next range (two shared-memory words) when the current one is used up, so a warp runs for as long as its
-    // busiest lane has candidates.  With nested per-row loops it ran, row by row, for the longest run of any lane (ncu:
-    // 12.5 of 32 lanes active, 77 candidate iterations per warp for ~10 candidates per lane).
-    auto test = [&](int j, unsigned code) {
-        const SAtom o = load_satom(fr + j);
-        double dx = o.x - mex, dy = o.y - mey, dz = o.z - mez;
-        if (code != (13u << 24)) {                  // P3: (pj - pi) + T, T = (s0*a + s1*b) + s2*c (x + 0.0 == x: the home image skips the adds)
-            const int c = (int)(code >> 24), s0 = c % 3 - 1, s1 = (c / 3) % 3 - 1, s2 = c / 9 - 1;
-            const double fs0 = (double)s0, fs1 = (double)s1, fs2 = (double)s2;
-            dx += (fs0 * G.cell[0] + fs1 * G.cell[3]) + fs2 * G.cell[6];
-            dy += (fs0 * G.cell[1] + fs1 * G.cell[4]) + fs2 * G.cell[7];
-            dz += (fs0 * G.cell[2] + fs1 * G.cell[5]) + fs2 * G.cell[8];
-        }
-        const double dd = (dx * dx + dy * dy) + dz * dz;
-        if (dd < a.r2search) {
-            const int sj = (int)(o.s & 0xff);
-            if (dd < __ldg(a.cn_thr2 + krow[sj])) {
+    // One cell list per species (n_lists > 1): only the lists of the species this atom has a positive cutoff with are visited --
+    // on the ZIF 'Zn-N' analysis an N atom looks at the Zn list alone (one candidate in five of the mixed list).
+    const int ncell = nc0 * nc1 * nc2;
+    const unsigned pmask = a.n_lists > 1 ? (unsigned)a.partner_mask[si] : 1u;
+    __shared__ int2 s_rng[BAD_RANGES][128];          // [range][thread]: first candidate, end | image code << 24
+    for (unsigned left = pmask; left; left &= left - 1) {
+        const int sj_list = __ffs(left) - 1;             // partner species (or 0: the single list)
+        const uint32_t *csl = a.n_lists > 1 ? cs + (int)a.list_of[sj_list] * ncell : cs;
+        const double thr_list = a.n_lists > 1 ? __ldg(a.cn_thr2 + krow[sj_list]) : 0.0;
+        auto test = [&](int j, unsigned code) {
+            const SAtom o = load_satom(fr + j);
+            double dx = o.x - mex, dy = o.y - mey, dz = o.z - mez;
+            if (code != (13u << 24)) {                  // P3: (pj - pi) + T, T = (s0*a + s1*b) + s2*c (x + 0.0 == x: the home image skips the adds)
+                const int c = (int)(code >> 24), s0 = c % 3 - 1, s1 = (c / 3) % 3 - 1, s2 = c / 9 - 1;
+                const double fs0 = (double)s0, fs1 = (double)s1, fs2 = (double)s2;
+                dx += (fs0 * G.cell[0] + fs1 * G.cell[3]) + fs2 * G.cell[6];
+                dy += (fs0 * G.cell[1] + fs1 * G.cell[4]) + fs2 * G.cell[7];
+                dz += (fs0 * G.cell[2] + fs1 * G.cell[5]) + fs2 * G.cell[8];
+            }
+            const double dd = (dx * dx + dy * dy) + dz * dz;
+            bool hit;
+            if (a.n_lists > 1) hit = dd < thr_list;      // every atom of the list has the partner species
+            else hit = dd < a.r2search && dd < __ldg(a.cn_thr2 + krow[(int)(o.s & 0xff)]);
+            if (hit) {
                 if (nn < BAD_NB_MAX) nb[nn++] = (unsigned)j | code;
                 else overflow = true;
             }
-        }
-    };
-    __shared__ int2 s_rng[BAD_RANGES][128];          // [range][thread]: first candidate, end | image code << 24
-    if (!many_wraps && m0 == 1 && m1 == 1 && nz <= 2) {
-        const int tid = threadIdx.x;
+        };
+        if (!many_wraps && m0 == 1 && m1 == 1 && nz <= 2) {
+            // Two steps.  A) every lane lists its candidate ranges -- (row, z run) -> [first, end) | image code -- in shared memory,
+            // in lockstep (nine rows, one or two z runs each).  B) ONE flat loop over the candidates of all its ranges: a lane
+            // opens its next range (two shared-memory words) when the current one is used up, so a warp runs for as long as its
+            // busiest lane has candidates.  With nested per-row loops it ran, row by row, for the longest run of any lane (ncu:
+            // 12.5 of 32 lanes active, 77 candidate iterations per warp for ~10 candidates per lane).
+            const int tid = threadIdx.x;
+            int cnt = 0;                                  // ranges that hold at least one atom (half of them are empty at ~0.3 atoms per cell)
 #pragma unroll
-        for (int row = 0; row < 9; ++row) {
-            int s0, q0, s1, q1;
-            wrap_cell(c0 + row / 3 - 1, nc0, s0, q0);
-            wrap_cell(c1 + row % 3 - 1, nc1, s1, q1);
-            const int rowbase = (q0 * nc1 + q1) * nc2;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                int2 e = make_int2(0, 0);
-                if (k < nz) {
-                    e.x = (int)cs[rowbase + zq[k]];
-                    e.y = (int)cs[rowbase + zq[k] + zl[k]] | (((s0 + 1) + 3 * (s1 + 1) + 9 * (zs[k] + 1)) << 24);
-                }
-                s_rng[row * 2 + k][tid] = e;
-            }
-        }
-        int rg = -1, j = 0, je = 0;
-        unsigned code = 0;
-        for (;;) {
-            while (j >= je && rg < BAD_RANGES - 1) {     // open the next range
-                const int2 e = s_rng[++rg][tid];
-                j = e.x; je = e.y & 0xffffff; code = (unsigned)e.y & 0xff000000u;
-            }
-            if (j >= je) break;
-            if (!(code == (13u << 24) && j == i)) test(j, code);      // skip the zero-shift self pair
-            ++j;
-        }
-    } else {
-        for (int d0 = -m0; d0 <= m0; ++d0) {
-            int s0, q0;
-            wrap_cell(c0 + d0, nc0, s0, q0);
-            for (int d1 = -m1; d1 <= m1; ++d1) {
-                int s1, q1;
-                wrap_cell(c1 + d1, nc1, s1, q1);
+            for (int row = 0; row < 9; ++row) {
+                int s0, q0, s1, q1;
+                wrap_cell(c0 + row / 3 - 1, nc0, s0, q0);
+                wrap_cell(c1 + row % 3 - 1, nc1, s1, q1);
                 const int rowbase = (q0 * nc1 + q1) * nc2;
-                for (int d2 = -m2; d2 <= m2;) {
-                    int s2, q2;
-                    wrap_cell(c2 + d2, nc2, s2, q2);
-                    const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
-                    const unsigned code = (unsigned)((s0 + 1) + 3 * (s1 + 1) + 9 * (s2 + 1)) << 24;
-                    for (int j = (int)cs[rowbase + q2]; j < (int)cs[rowbase + q2 + len]; ++j)
-                        if (!(code == (13u << 24) && j == i)) test(j, code);
-                    d2 += len;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k < nz) {
+                        const int first = (int)csl[rowbase + zq[k]], end = (int)csl[rowbase + zq[k] + zl[k]];
+                        if (end > first) {
+                            s_rng[cnt][tid] = make_int2(first, end | (((s0 + 1) + 3 * (s1 + 1) + 9 * (zs[k] + 1)) << 24));
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+            int rg = 0, j = 0, je = 0;
+            unsigned code = 0;
+            for (;;) {
+                if (j >= je) {                            // open the next range (never empty)
+                    if (rg >= cnt) break;
+                    const int2 e = s_rng[rg++][tid];
+                    j = e.x; je = e.y & 0xffffff; code = (unsigned)e.y & 0xff000000u;
+                }
+                if (!(code == (13u << 24) && j == i)) test(j, code);      // skip the zero-shift self pair
+                ++j;
+            }
+        } else {
+            for (int d0 = -m0; d0 <= m0; ++d0) {
+                int s0, q0;
+                wrap_cell(c0 + d0, nc0, s0, q0);
+                for (int d1 = -m1; d1 <= m1; ++d1) {
+                    int s1, q1;
+                    wrap_cell(c1 + d1, nc1, s1, q1);
+                    const int rowbase = (q0 * nc1 + q1) * nc2;
+                    for (int d2 = -m2; d2 <= m2;) {
+                        int s2, q2;
+                        wrap_cell(c2 + d2, nc2, s2, q2);
+                        const int len = min(m2 - d2, nc2 - 1 - q2) + 1;
+                        const unsigned code = (unsigned)((s0 + 1) + 3 * (s1 + 1) + 9 * (s2 + 1)) << 24;
+                        for (int j = (int)csl[rowbase + q2]; j < (int)csl[rowbase + q2 + len]; ++j)
+                            if (!(code == (13u << 24) && j == i)) test(j, code);
+                        d2 += len;
+                    }
                 }
             }
         }
@@ -184,8 +207,18 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad_search(BadArgs a) {
     if (nn < 2) return;
     // a centre: reserve a run of the pool and write the P3 image vectors (re-formed with the same operations on the same
     // operands: the same doubles as in the walk); they are normalised by the angle kernel, where every lane is a centre
-    const unsigned off = atomicAdd(a.counters + 1, (unsigned)nn);
-    if (off + (unsigned)nn > a.pool_cap) { atomicOr(a.flags, 4); return; }
+    // one reservation per warp: the centres of a warp take consecutive runs of the pool and consecutive records of the centre list
+    // (two same-address atomics per CENTRE -- 1.7 M per batch on C4 -- would be the kernel's longest queue)
+    cg::coalesced_group grp = cg::coalesced_threads();
+    const unsigned before = cg::exclusive_scan(grp, (unsigned)nn);
+    unsigned off = 0, ci = 0;
+    if (grp.thread_rank() == grp.size() - 1) {
+        off = atomicAdd(a.counters + 1, before + (unsigned)nn);
+        ci = atomicAdd(a.counters, (unsigned)grp.size());
+    }
+    off = grp.shfl(off, grp.size() - 1) + before;
+    ci = grp.shfl(ci, grp.size() - 1) + grp.thread_rank();
+    if (off + (unsigned)nn > a.pool_cap) { atomicOr(a.flags, 4); nn = 0; off = 0; }      // the record below stays valid (no neighbours); finish reports the overflow
     for (int p = 0; p < nn; ++p) {
         const int j = (int)(nb[p] & 0xffffffu), code = (int)(nb[p] >> 24);
         const SAtom o = load_satom(fr + j);
@@ -201,7 +234,6 @@ __global__ void __launch_bounds__(128, BAD_MIN_BLOCKS) k_bad_search(BadArgs a) {
         r.ux = dx; r.uy = dy; r.uz = dz; r.sp = (long long)(o.s & 0xff);
         a.pool[off + p] = r;
     }
-    const unsigned ci = atomicAdd(a.counters, 1u);
     BadCentre c;
     c.off = off; c.nn = (unsigned short)nn; c.sp = (unsigned char)si; c.pad = 0;
     a.centres[ci] = c;

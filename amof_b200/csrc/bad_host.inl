@@ -17,6 +17,7 @@ struct BadState {
     int n_slots = 0, tthr_smem = 0, angle_grid = 0;
     size_t angle_smem = 0;
     unsigned long long centre_mask[AMOFB_MAX_SPECIES];
+    uint16_t partner_mask[AMOFB_MAX_SPECIES];     // species with a positive cutoff to this one
 };
 
 static void bad_release(amofb_ctx *ctx) {
@@ -162,7 +163,17 @@ extern "C" int amofb_bad_begin(amofb_ctx *ctx, int n_atoms, int n_species, const
         for (int x = 0; x < S; ++x)
             for (int y = 0; y < S; ++y)
                 if (cutoff[x * S + y] > 0.0) keep[x] = 1;
-        if ((rc = batcher_set_filter(ctx, p->bt, species, keep))) return fail(rc);
+        if ((rc = batcher_set_filter(ctx, p->bt, species, keep, env_int("AMOFB_BAD_NO_CENTRE_LIST", 0) ? nullptr : p->centre_mask))) return fail(rc);
+        // one cell list per kept species, and for every species the partners it has a positive cutoff with
+        memset(p->partner_mask, 0, sizeof p->partner_mask);
+        int nl = 0;
+        for (int x = 0; x < S; ++x) {
+            if (keep[x]) p->bt.list_of[x] = (uint8_t)nl++;
+            for (int y = 0; y < S; ++y)
+                if (cutoff[x * S + y] > 0.0) p->partner_mask[x] |= (uint16_t)(1u << y);
+        }
+        p->bt.n_lists = (nl > 1 && !env_int("AMOFB_BAD_ONE_LIST", 0)) ? nl : 1;
+        if (p->bt.n_lists == 1) memset(p->bt.list_of, 0, sizeof p->bt.list_of);
     }
     const size_t hist_n = (size_t)n_triples * (AMOFB_BAD_MAX_CN + 1) * nbins;
     if ((rc = dev_alloc(ctx, &p->d_cnthr2, cnthr.size()))) return fail(rc);
@@ -237,6 +248,10 @@ static int bad_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool o
         a.hist = p->d_hist; a.dropped = p->d_dropped; a.flags = p->d_flags;
         a.n_keep = b.n_keep;
         a.centre_mask = p->d_centre_mask;
+        a.centre_list = b.d_centre_list; a.n_centres = b.n_centres;
+        a.n_lists = b.n_lists;
+        memcpy(a.list_of, b.list_of, sizeof a.list_of);
+        memcpy(a.partner_mask, p->partner_mask, sizeof a.partner_mask);
         a.r2search = p->r2search; a.inv_dtheta_f = (float)(1.0 / p->dtheta);
         a.n_atoms = b.n_atoms; a.n_frames = nf; a.n_species = p->n_species; a.nkeys = p->nkeys;
         a.n_triples = p->n_triples; a.nbins = p->nbins;
@@ -245,7 +260,9 @@ static int bad_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool o
         long long total = (long long)nf * b.n_keep;
         if (total > 0) {
             CUDA_TRY(ctx, cudaMemsetAsync(p->d_counters, 0, sizeof(unsigned) * 2, ctx->s_compute));
-            k_bad_search<<<(unsigned)((total + 127) / 128), 128, 0, ctx->s_compute>>>(a);   // one thread per atom of the filtered, cell-sorted frames
+            // one thread per possible centre (compact list written by the scatter kernel), or per atom of the filtered, cell-sorted frames
+            const long long nsearch = b.d_centre_list ? (long long)nf * b.n_centres : total;
+            if (nsearch > 0) k_bad_search<<<(unsigned)((nsearch + 127) / 128), 128, 0, ctx->s_compute>>>(a);
             k_bad_angles<<<p->angle_grid, 256, p->angle_smem, ctx->s_compute>>>(a);         // one thread per centre found
             ctx->launches += 2;
             CUDA_TRY(ctx, cudaGetLastError());

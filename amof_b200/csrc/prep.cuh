@@ -42,6 +42,17 @@ struct PrepArgs {
     uint32_t *orig;                // optional [F*N]: original atom index of every sorted atom (explicit neighbour lists)
     int *wraps;                    // optional [F*N][3]: cell translations removed from every sorted atom by P2
     uint32_t *slot;                // optional [F*N]: position of every atom in its frame's sorted order (pair lists)
+    // optional (bond angles): a compact list of the atoms that can be the centre of an angle, so that the search kernel has a
+    // thread per CENTRE instead of one per kept atom: centre_rank[n_keep] = rank among the centres of a frame or -1,
+    // centre_list[F * n_centres] receives frame * n_keep + position in the sorted frame
+    const int *centre_rank;
+    unsigned *centre_list;
+    int n_centres;
+    // optional (bond angles): one cell list PER SPECIES, laid end to end: list_of[species] = which list an atom goes to; the cell
+    // index becomes list * ncell + cell and cell_start holds n_lists * ncell + 1 entries per frame.  A search then only visits
+    // the lists of the species it has a positive cutoff with.  n_lists = 1 and list_of = 0 everywhere else.
+    int n_lists;
+    uint8_t list_of[AMOFB_MAX_SPECIES];
 };
 
 // wn (optional): the integer cell translations w_k = floor(f_k) that P2 removed
@@ -80,6 +91,7 @@ __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
         int c[3];
         wrap_atom(g, a.raw + 3 * ((long long)f * a.n_atoms + i), pw, c);
         uint32_t cid = (uint32_t)((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+        if (a.n_lists > 1) cid += (uint32_t)a.list_of[a.species[i]] * (uint32_t)g.ncell;
         a.cid[idx] = cid;
         a.rank[idx] = atomicAdd(&a.cell_count[g.cs_off + cid], 1u);
     }
@@ -95,7 +107,7 @@ __global__ void __launch_bounds__(1024) k_cell_scan(PrepArgs a) {
     const FrameGeom &g = a.geom[f];
     const uint32_t *cnt = a.cell_count + g.cs_off;
     uint32_t *out = a.cell_start + g.cs_off;
-    int n = g.ncell;
+    int n = g.ncell * a.n_lists;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarp = blockDim.x >> 5;
     uint32_t carry = 0;
@@ -156,6 +168,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
          idx += (long long)gridDim.x * blockDim.x) {
         int f = (int)(idx / per);
         int i = (int)(idx - (long long)f * per);
+        const int kk = i;
         if (a.keep_idx) i = a.keep_idx[i];
         if (a.cid[idx] == 0xffffffffu) continue;          // filtered out by species_keep
         const FrameGeom &g = a.geom[f];
@@ -163,6 +176,10 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         int c[3], wn[3];
         wrap_atom(g, a.raw + 3 * ((long long)f * a.n_atoms + i), pw, c, wn);
         uint32_t dst = a.cell_start[g.cs_off + a.cid[idx]] + a.rank[idx];
+        if (a.centre_list) {
+            const int cr = a.centre_rank[kk];
+            if (cr >= 0) a.centre_list[(long long)f * a.n_centres + cr] = (unsigned)((long long)f * per + dst);
+        }
         SAtom s;
         s.x = pw[0]; s.y = pw[1]; s.z = pw[2];
         // species | c0 << 8 | c1 << 20 | c2 << 32   (nc <= 1024 per axis)

@@ -28,7 +28,9 @@ for name, frames in (("c2", 5), ("c1", 9), ("c3", 2)):
 walk = synth.make_trajectory("c1", 101)
 amof_b200.msd.WindowMsd.from_trajectory(walk, delta_time=5, timestep=1, mutate=False)
 amof_b200.msd.WindowMsd.from_trajectory(walk, delta_time=5, timestep=1, mutate=False, unwrap=True)
-amof_b200.msd.DirectMsd.from_trajectory(walk)
+ortho = amof_b200.ArrayTrajectory(walk.numbers, walk.positions, np.diag(np.diag(walk.cells[0])))
+amof_b200.msd.DirectMsd.from_trajectory(ortho)          # DirectMsd only takes orthogonal cells
+amof_b200.msd.WindowMsd.from_trajectory(ortho, delta_time=5, timestep=1, mutate=False)
 n = backend.ctx.guard_violations()           # every analysis has returned its blocks by now
 print("guard violations:", n)
 assert n == 0
