@@ -413,9 +413,14 @@ static int batcher_set_filter(amofb_ctx *ctx, Batcher &b, const uint8_t *species
         int nc = 0;
         for (size_t k = 0; k < idx.size(); ++k) crank[k] = centre_mask[species[idx[k]]] ? nc++ : -1;
         b.n_centres = nc;
-        AMOFB_TRY(dev_alloc(ctx, &b.d_centre_rank, crank.size()));
-        CUDA_TRY(ctx, cudaMemcpy(b.d_centre_rank, crank.data(), sizeof(int) * crank.size(), cudaMemcpyHostToDevice));
-        AMOFB_TRY(dev_alloc(ctx, &b.d_centre_list, (size_t)std::max(nc, 1) * (size_t)b.cap_frames));
+        // every kept atom a possible centre (Bad on 'Zn-N' asks for N-Zn-N and Zn-N-Zn): a list would only replace the cell order of
+        // the threads by the file order (measured on C4: 277 k instead of 311 k frames/s)
+        if (nc == (int)idx.size()) b.n_centres = 0;
+        else {
+            AMOFB_TRY(dev_alloc(ctx, &b.d_centre_rank, crank.size()));
+            CUDA_TRY(ctx, cudaMemcpy(b.d_centre_rank, crank.data(), sizeof(int) * crank.size(), cudaMemcpyHostToDevice));
+            AMOFB_TRY(dev_alloc(ctx, &b.d_centre_list, (size_t)std::max(nc, 1) * (size_t)b.cap_frames));
+        }
     }
     AMOFB_TRY(dev_alloc(ctx, &b.d_species_keep, (size_t)AMOFB_MAX_SPECIES));
     CUDA_TRY(ctx, cudaMemcpy(b.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice));

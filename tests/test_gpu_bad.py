@@ -65,6 +65,26 @@ def test_random_boxes(backend, seed, n, tri, size, dtheta):
     assert nf == T
 
 
+@pytest.mark.parametrize("triples", [[(0, 1)], [(0, 1), (2, 1)], [(1, -1)], [(2, 2), (0, 1)]])
+@pytest.mark.parametrize("one_list", [False, True])
+def test_centre_list_and_species_lists(backend, monkeypatch, triples, one_list):
+    """Only some of the kept species are centres: the search then runs over the compact centre list the scatter kernel writes
+    (one thread per possible centre), and with one cell list per species it visits the lists of the partner species only.
+    Both against the oracle, and the single mixed list (AMOFB_BAD_ONE_LIST) against the same numbers."""
+    S, T = 3, 3
+    frames = [random_box(77 + f, 600, S, True, 15.0, scale_pos=2.0) for f in range(T)]
+    spec = frames[0][2]
+    pos = np.array([f[0] for f in frames])
+    cell = np.array([f[1] for f in frames])
+    cut = np.array([[2.6, 3.0, 0.0], [3.0, 0.0, 2.8], [0.0, 2.8, 2.4]])
+    if one_list:
+        monkeypatch.setenv("AMOFB_BAD_ONE_LIST", "1")
+    hist, dropped, nf = backend.bad_counts(spec, S, [(pos, cell)], cut, triples, 0.5, 361)
+    want, wdrop = _oracle(pos, cell, spec, S, cut, triples, 0.5, 361)
+    assert int(want.sum()) > 20 and nf == T
+    assert np.array_equal(hist, want) and np.array_equal(dropped, wdrop)
+
+
 @pytest.mark.parametrize("tri", [False, True])
 def test_species_without_cutoffs_are_filtered(backend, tri):
     """Species that appear in no cutoff pair never enter the cell list (PrepArgs::species_keep): the counts of the
