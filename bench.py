@@ -471,7 +471,8 @@ class MsdWorkload:
         from amof_b200 import frames as fr, msd
         if not hasattr(self, "traj"):
             ctx = self.backend.ctx
-            nslab = max(1, min(self.T, 256, (3 << 29) // (24 * self.n_total)))
+            n_local = -(-self.n_total // self.world)         # the library sizes its slabs by the atoms a rank holds
+            nslab = max(1, min(self.T, 256, (3 << 29) // (24 * n_local)))
             nslab = nslab - nslab % 32 if nslab >= 32 else nslab          # the library's own slab size: blocks are served as views
             rng = np.random.default_rng(5)
             slabbuf = ctx.pinned_empty((nslab, self.n_total, 3))

@@ -2,7 +2,7 @@
 O=gpurun_out/bench2; mkdir -p $O
 nvidia-smi -L | head -4
 timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q 2>&1 | tail -5
-( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err ) 2> $O/time_n2.txt
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > $O/bench_n2.json 2> $O/bench_n2.err ) 2> $O/time_n2.txt
 tail -5 $O/bench_n2.err; tail -3 $O/time_n2.txt
 python - <<'PY'
 import json
