@@ -693,93 +693,9 @@ __global__ void __launch_bounds__(COMMIT_THREADS, 3) k_msd_slab_commit(const dou
     }
 }
 
-// Register version (round 2; ncu of the kernel above: 7 barriers per round, the serial scan -- half of the block idle -- holds
-// 37 % of the stall samples, 3.2 TB/s).  A lane owns one (atom, component) COLUMN for the whole slab: previous position and
-// running sum stay in registers.  A warp holds 10 atoms (30 lanes: the three components of an atom are neighbouring lanes, so
-// the wrap's 3x3 products take the other components by shuffle; 2 lanes idle), a block 12 warps = 120 atoms.  Per round of
-// REGF frames: REGF independent loads per lane (240-byte runs per warp and frame, the warps of a block back to back), then
-// shift -> difference -> wrap -> running sum in registers, the sums into a padded tile, ONE barrier, and the transposed
-// write-out (half a warp per column: 128-byte runs of the atom-major store).  Two tiles alternate, so the write-out of a round
-// overlaps the loads of the next.  Expressions and order are those of wrap_disp / wrap_disp_diag: the same bits.
-#define REGF 16
-#define REG_THREADS 384
-#define REG_ATOMS (10 * (REG_THREADS / 32))
-#define REG_COLS (3 * REG_ATOMS)
-#define REG_LD (REG_COLS + 1)
-#define REG_COM_MAX 256                   // frames per host slab (stage_frames is at most 256); longer device slabs take the kernel above
-#define REG_SMEM (sizeof(double) * (2 * REGF * REG_LD + 3 * REG_COM_MAX))
-template <int CELL>      // 0 = one cell per frame, 1 = the same cell in every frame, 2 = the same orthorhombic cell
-__global__ void __launch_bounds__(REG_THREADS, 2) k_msd_slab_commit_reg(const double *__restrict__ slab, double *__restrict__ P,
-                                                                        const MsdGeom *__restrict__ geom, const double *__restrict__ com,
-                                                                        double *__restrict__ carry, int n, int Tp, int first, int count) {
-    extern __shared__ __align__(16) double reg_sm[];
-    double *s_com = reg_sm + 2 * REGF * REG_LD;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int a0 = blockIdx.x * REG_ATOMS, na = min(REG_ATOMS, n - a0), ncol = 3 * na;
-    const int comp = lane % 3, base = lane - comp;            // lanes 30, 31: comp 0 / 1 of a phantom atom, never `mine`
-    const int col = 30 * warp + lane;
-    const bool mine = lane < 30 && col < ncol;
-    const size_t cat = (size_t)(a0 + col / 3) * 6 + (size_t)comp;
-    double prev = (mine && first > 0) ? carry[cat] : 0.0, run = (mine && first > 0) ? carry[cat + 3] : 0.0;
-    const double shift = (0.0 - 0.5) - 1e-7;
-    double i0 = 0.0, i1 = 0.0, i2 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;     // inverse column `comp`, cell column `comp`
-    if (CELL != 0) {
-        i0 = geom[0].inv[comp]; i1 = geom[0].inv[3 + comp]; i2 = geom[0].inv[6 + comp];
-        c0 = geom[0].cell[comp]; c1 = geom[0].cell[3 + comp]; c2 = geom[0].cell[6 + comp];
-    }
-    for (int i = tid; i < 3 * count; i += REG_THREADS) s_com[i] = com[i];
-    __syncthreads();
-    const double *src = slab + (size_t)a0 * 3 + col;
-    const size_t fstride = (size_t)n * 3;
-    int buf = 0;
-    for (int k0 = 0; k0 < count; k0 += REGF, buf ^= 1) {
-        const int nr = min(REGF, count - k0);
-        double *tile = reg_sm + (size_t)buf * REGF * REG_LD;
-        double v[REGF];
-#pragma unroll
-        for (int r = 0; r < REGF; ++r) v[r] = (mine && r < nr) ? src[(size_t)(k0 + r) * fstride] : 0.0;
-#pragma unroll
-        for (int r = 0; r < REGF; ++r) {
-            if (r < nr) {                                       // uniform over the block: the shuffles below are convergent
-                const int k = first + k0 + r;
-                const double x = v[r] - s_com[3 * (k0 + r) + comp];      // translate(-cg), msd.py:237
-                const double e = x - prev;
-                prev = x;
-                if (k > 0) {                                    // delta_0 = 0: the running sum is taken relative to the first frame
-                    double d;
-                    const double ex = __shfl_sync(0xffffffffu, e, base), ey = __shfl_sync(0xffffffffu, e, base + 1),
-                                 ez = __shfl_sync(0xffffffffu, e, min(base + 2, 31));
-                    if (CELL == 0) {
-                        const MsdGeom &G = geom[k - 1];         // cell of frame k-1 wraps k-1 -> k
-                        i0 = G.inv[comp]; i1 = G.inv[3 + comp]; i2 = G.inv[6 + comp];
-                        c0 = G.cell[comp]; c1 = G.cell[3 + comp]; c2 = G.cell[6 + comp];
-                    }
-                    double g;
-                    if (CELL == 2) g = np_mod1(e * (comp == 0 ? i0 : comp == 1 ? i1 : i2) - shift) + shift;      // wrap_disp_diag: the diagonal entry
-                    else g = np_mod1(((ex * i0 + ey * i1) + ez * i2) - shift) + shift;
-                    if (CELL == 2) d = g * (comp == 0 ? c0 : comp == 1 ? c1 : c2);
-                    else {
-                        const double g0 = __shfl_sync(0xffffffffu, g, base), g1 = __shfl_sync(0xffffffffu, g, base + 1),
-                                     g2 = __shfl_sync(0xffffffffu, g, min(base + 2, 31));
-                        d = (g0 * c0 + g1 * c1) + g2 * c2;
-                    }
-                    run += d;
-                }
-                if (mine) tile[r * REG_LD + col] = run;
-            }
-        }
-        __syncthreads();        // the tile is complete; the other tile's write-out (previous round) was finished by everyone who got here
-        {
-            const int f = lane & 15, half = lane >> 4;
-            if (f < nr) {
-                double *dst = P + (size_t)a0 * 3 * Tp + (size_t)(first + k0 + f);
-                for (int cc = 2 * warp + half; cc < ncol; cc += 2 * (REG_THREADS / 32)) dst[(size_t)cc * Tp] = tile[f * REG_LD + cc];
-            }
-        }
-        // no second barrier: the next round fills the OTHER tile, and the round after that passes the barrier above first
-    }
-    if (mine) { carry[cat] = prev; carry[cat + 3] = run; }
-}
+// (A register version -- a lane per (atom, component) column for the whole slab, the other components by shuffle, carry in registers, one
+// barrier per round -- gave the same bits and was slower: 9.1-9.8 against 8.85 ms per 100 000 atoms x 5 000 frames;
+// experiments/csrc/msd_commit_reg.cuh.)
 
 // One component of one atom at a time: |R_k - R_j|^2 and R_k . R_j are sums over x, y, z, so the block stages 8*Tp bytes
 // instead of 24*Tp, several blocks share an SM, and one block's bulk copy and barriers hide behind the others' tiles.

@@ -262,29 +262,6 @@ def test_wide_window_kernel_shapes(backend, monkeypatch, T, n, delta, kb, nwt):
     np.testing.assert_allclose(narrow, want, rtol=RTOL, atol=1e-13)
 
 
-@pytest.mark.parametrize("T,n,slab,device,cellmode", [
-    (150, 300, 40, False, 2), (97, 129, 97, True, 2), (64, 5, 16, False, 2),
-    (150, 300, 40, False, 1), (97, 121, 97, True, 1), (70, 250, 32, False, 0), (33, 10, 7, True, 0)])
-def test_register_commit_matches_block_commit(backend, monkeypatch, T, n, slab, device, cellmode):
-    """k_msd_slab_commit_reg (a lane per (atom, component) column, the other components by shuffle, carry in registers) must give
-    the bits of k_msd_slab_commit -- same expressions, same order of the running sum -- for one orthorhombic cell (2), one
-    triclinic cell (1) and a cell per frame (0)."""
-    S = 3
-    pos, cells, spec, masses = _walk(1300 + T, T, n, cellmode != 2)
-    if cellmode == 2:
-        cells[:] = np.diag(np.diag(cells[0]))
-    elif cellmode == 1:
-        cells[:] = cells[0]
-    window = np.arange(0, T // 2, 3)
-    col, com1 = _gpu_stream(backend, pos, cells, spec, masses, S, window, slab, device)
-    monkeypatch.setenv("AMOFB_MSD_NO_COLUMN_COMMIT", "1")
-    blk, com2 = _gpu_stream(backend, pos, cells, spec, masses, S, window, slab, device)
-    assert np.array_equal(col, blk, equal_nan=True) and np.array_equal(com1, com2)
-    want, _ = orc.msd_window(pos, cells, masses, spec, S, window)
-    present = np.bincount(spec, minlength=S) > 0
-    np.testing.assert_allclose(col[present], want[present], rtol=RTOL, atol=1e-13)
-
-
 def test_streaming_forms_agree_and_fall_back(backend, monkeypatch):
     """The autocorrelation form must agree with the difference form, and a request whose windows are small against the
     squares they are taken from (ballistic drift, lag 1) must come out right all the same (the library re-runs it in the
