@@ -606,10 +606,15 @@ __global__ void __launch_bounds__(256) k_msd_slab_sums(const double *__restrict_
     }
 }
 
-#define COMMIT_A 64                       // atoms per block: 1 536-byte runs of every frame row
+#ifndef COMMIT_A
+#define COMMIT_A 32                       // atoms per block: 768-byte runs of every frame row (64 atoms x 384 threads: 8.86, 32 x 192: 8.53,
+                                          // 16 x 96: 8.47, 128 x 384: 11.6 ms of ingest per 100 000 atoms x 5 000 frames)
+#endif
 #define COMMIT_FS 32                      // frames per round: 256-byte runs of every output row
 #define COMMIT_LD (3 * COMMIT_A + 1)      // odd row stride: the column reads of the write-out are conflict-free
-#define COMMIT_THREADS 384
+#ifndef COMMIT_THREADS
+#define COMMIT_THREADS 192                // two frame rows of the block's 96 columns per load pass; 6 blocks per SM
+#endif
 #define COMMIT_ITEMS ((COMMIT_FS * COMMIT_A + COMMIT_THREADS - 1) / COMMIT_THREADS)
 #define COMMIT_SMEM (sizeof(double) * (COMMIT_FS * COMMIT_LD + 6 * COMMIT_A))      // above the 48 KB static limit: opt-in
 
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(256) k_msd_slab_sums(const double *__restrict_
 // (A variant that kept the rows of round r+1 in flight with 8-byte cp.async copies into a second buffer was slower:
 // 12.1 instead of 10.3 ms per 100 000 atoms x 5 000 frames; the plain loads below already have 16 rows in flight per thread.)
 template <int CELL>      // 0 = one cell per frame, 1 = the same cell in every frame, 2 = the same orthorhombic cell
-__global__ void __launch_bounds__(COMMIT_THREADS, 3) k_msd_slab_commit(const double *__restrict__ slab, double *__restrict__ P,
+__global__ void __launch_bounds__(COMMIT_THREADS, 1152 / COMMIT_THREADS) k_msd_slab_commit(const double *__restrict__ slab, double *__restrict__ P,
                                                                       const MsdGeom *__restrict__ geom, const double *__restrict__ com,
                                                                       double *__restrict__ carry, int n, int Tp, int first, int count) {
     extern __shared__ __align__(16) double commit_sm[];          // COMMIT_SMEM bytes
