@@ -12,6 +12,11 @@
 //   k_msd_frame_sums  per-frame weighted sums over atoms (centre of mass; DirectMsd totals), deterministic 2-stage
 //   k_msd_window      persistent blocks; per atom: series -> smem (SoA), all windows, per-species partial sums
 //   k_msd_direct      DirectMsd recurrence (orthogonal cells, msd.py:81-105), one thread per atom
+// and, further down, the STREAMING path of WindowMsd(unwrap=False) -- what the headline C5 number runs on:
+//   k_msd_slab_sums / k_msd_slab_commit   ingest: per-frame mass sums; shift, wrap, running sum and transposition into an
+//                     atom-major store of three arrays x[Tp] | y[Tp] | z[Tp] per atom, relative to the first frame
+//   k_msd_window_wide autocorrelation form on wide register tiles, two series buffers filled by bulk copies, no block barrier
+//   k_msd_window_soa  its narrow predecessor: difference form (fallback) and series too long for two buffers
 //
 // MSD is compared at 1e-12 relative (north_star), not bit-exactly: running sums are warp scans and the squared
 // norms use explicit FMAs.  The wrap itself follows P8 operation by operation.
@@ -816,7 +821,7 @@ __device__ __forceinline__ void msd_wide_first(int s, unsigned sb, const char *s
     }
 }
 
-#define MSD_WIDE_THREADS 512
+#define MSD_WIDE_THREADS 512       // resident threads per SM the kernel is built for: THREADS = 256 -> two blocks
 #ifndef MSD_WIDE_WAIT_NS
 #define MSD_WIDE_WAIT_NS 4000       // suspend-time hint of the series wait (0: plain try_wait spin)
 #endif
