@@ -20,6 +20,7 @@ if os.environ.get("AMOFB_LIB"):          # a variant built by tools/build_varian
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 214
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+nbins = int(sys.argv[4]) if len(sys.argv) > 4 else 999        # fewer bins leave more shared memory to a tile's atoms
 backend = _lib.get_backend()
 ctx = backend.ctx
 traj = synth.make_trajectory(name, T)
@@ -30,7 +31,7 @@ ctx.h2d(dev, traj.positions)
 ctx.set_profiling(True)
 for r in range(reps):
     t0 = time.perf_counter()
-    res = backend.pair_counts(spec, len(zs), [(dev.value, traj.cells)], rmax=10.0, nbins=999, cn_cutoff=cut)
+    res = backend.pair_counts(spec, len(zs), [(dev.value, traj.cells)], rmax=10.0, nbins=nbins, cn_cutoff=cut)
     dt = time.perf_counter() - t0
     ms, n = ctx.pair_kernel_time(reset=True)
     print("rep %d: %.1f ms wall, pair kernels %.3f ms over %d launches, %d pairs" % (r, dt * 1e3, ms, n, int(res["hist"].sum()) // 2))
