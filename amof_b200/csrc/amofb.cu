@@ -9,6 +9,7 @@
 #include "msd.cuh"
 
 #include <algorithm>
+#include <thread>
 #include <new>
 
 // ================================================================================================
@@ -337,6 +338,9 @@ struct Batcher {
     int *d_centre_rank = nullptr;        // optional (bond angles): rank of every kept atom among the possible centres of a frame, or -1
     unsigned *d_centre_list = nullptr;   //   and the compact list the scatter kernel fills: [cap_frames * n_centres]
     int n_centres = 0;
+    std::vector<int> keep_host;          // host copy of d_keep_idx
+    bool gather = false;                 // host frames: only the kept atoms cross PCIe (gathered into h_compact by host threads)
+    double *h_compact[2] = {nullptr, nullptr};      // per slot: [cap_frames][n_keep][3], page-locked
     int n_lists = 1;                     // cell lists per frame (bond angles: one per kept species)
     uint8_t list_of[AMOFB_MAX_SPECIES] = {0};
     bool want_orig = false;              // keep the original index of every sorted atom
@@ -358,6 +362,8 @@ static void batcher_release(amofb_ctx *ctx, Batcher &b) {
     }
     pool_put(ctx, b.d_species); pool_put(ctx, b.d_species_keep); pool_put(ctx, b.d_keep_idx);
     pool_put(ctx, b.d_centre_rank); pool_put(ctx, b.d_centre_list);
+    pool_put(ctx, b.h_compact[0]); pool_put(ctx, b.h_compact[1]);
+    b.h_compact[0] = b.h_compact[1] = nullptr;
     b.d_species = nullptr; b.d_species_keep = nullptr; b.d_keep_idx = nullptr; b.d_centre_rank = nullptr; b.d_centre_list = nullptr;
 }
 
@@ -422,6 +428,10 @@ static int batcher_set_filter(amofb_ctx *ctx, Batcher &b, const uint8_t *species
             AMOFB_TRY(dev_alloc(ctx, &b.d_centre_list, (size_t)std::max(nc, 1) * (size_t)b.cap_frames));
         }
     }
+    // frames in host memory: when under 60 % of the atoms are kept, host threads gather them and only they are copied (C4 'Zn-N':
+    // 29 % of 1.175 MB per frame; the kept atoms are single atoms between others, so a strided DMA would not do)
+    b.keep_host = idx;
+    b.gather = !idx.empty() && 10 * (long long)idx.size() < 6 * (long long)b.n_atoms && !env_int("AMOFB_NO_HOST_GATHER", 0);
     AMOFB_TRY(dev_alloc(ctx, &b.d_species_keep, (size_t)AMOFB_MAX_SPECIES));
     CUDA_TRY(ctx, cudaMemcpy(b.d_species_keep, keep, AMOFB_MAX_SPECIES, cudaMemcpyHostToDevice));
     AMOFB_TRY(dev_alloc(ctx, &b.d_keep_idx, idx.size() + 1));
@@ -441,6 +451,29 @@ static int batcher_harvest(amofb_ctx *ctx, Batcher &b, BatchSlot &s) {
     }
     s.frames = 0;
     return AMOFB_OK;
+}
+
+// out[f][k] = pos[f][keep[k]] for nf frames, split over host threads by frame
+static void host_gather_atoms(const double *pos, int nf, int n_atoms, const std::vector<int> &keep, double *out) {
+    const size_t nk = keep.size();
+    auto work = [&](int f0, int f1) {
+        for (int f = f0; f < f1; ++f) {
+            const double *src = pos + 3 * (size_t)f * n_atoms;
+            double *dst = out + 3 * (size_t)f * nk;
+            for (size_t k = 0; k < nk; ++k) {
+                const double *p = src + 3 * (size_t)keep[k];
+                dst[3 * k] = p[0]; dst[3 * k + 1] = p[1]; dst[3 * k + 2] = p[2];
+            }
+        }
+    };
+    unsigned hc = std::thread::hardware_concurrency();
+    int threads = (int)std::min<unsigned>(hc ? hc : 1u, 16u);
+    if (int f = env_int("AMOFB_HOST_THREADS", 0)) threads = f;
+    threads = std::max(1, std::min(threads, nf));
+    if (threads == 1) { work(0, nf); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work, (int)((long long)nf * t / threads), (int)((long long)nf * (t + 1) / threads));
+    for (auto &t : pool) t.join();
 }
 
 // Stage one batch (<= cap_frames frames): geometry, H2D (or adopt a device pointer) and the cell list.
@@ -463,6 +496,15 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     }
     const double *raw = pos;
     size_t bytes = sizeof(double) * 3 * (size_t)nf * b.n_atoms;
+    bool compact = false;
+    if (!pos_on_device && b.gather) {
+        double *&h = b.h_compact[b.next];
+        if (!h) AMOFB_TRY(pinned_alloc(ctx, &h, (size_t)b.cap_frames * b.n_keep * 3));
+        host_gather_atoms(pos, nf, b.n_atoms, b.keep_host, h);
+        pos = h;
+        bytes = sizeof(double) * 3 * (size_t)nf * b.n_keep;
+        compact = true;
+    }
     if (!pos_on_device) {
         CUDA_TRY(ctx, cudaMemcpyAsync(s.d_raw, pos, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
         CUDA_TRY(ctx, cudaEventRecord(s.ev_h2d, ctx->s_copy));
@@ -486,6 +528,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
     pa.centre_rank = b.d_centre_rank; pa.centre_list = b.d_centre_list; pa.n_centres = b.n_centres;
     pa.n_lists = b.n_lists;
     memcpy(pa.list_of, b.list_of, sizeof pa.list_of);
+    pa.raw_compact = compact ? 1 : 0;
     long long total = (long long)nf * (b.d_keep_idx ? b.n_keep : b.n_atoms);
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
     if (blocks < 1) blocks = 1;

@@ -53,6 +53,8 @@ struct PrepArgs {
     // the lists of the species it has a positive cutoff with.  n_lists = 1 and list_of = 0 everywhere else.
     int n_lists;
     uint8_t list_of[AMOFB_MAX_SPECIES];
+    // raw holds only the kept atoms of every frame, [F][n_keep][3] in keep_idx order (gathered on the host before the copy)
+    int raw_compact;
 };
 
 // wn (optional): the integer cell translations w_k = floor(f_k) that P2 removed
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256) k_cell_assign(PrepArgs a) {
         const FrameGeom &g = a.geom[f];
         double pw[3];
         int c[3];
-        wrap_atom(g, a.raw + 3 * ((long long)f * a.n_atoms + i), pw, c);
+        wrap_atom(g, a.raw + 3 * (a.raw_compact ? (long long)f * per + (idx - (long long)f * per) : (long long)f * a.n_atoms + i), pw, c);
         uint32_t cid = (uint32_t)((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
         if (a.n_lists > 1) cid += (uint32_t)a.list_of[a.species[i]] * (uint32_t)g.ncell;
         a.cid[idx] = cid;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(PrepArgs a) {
         const FrameGeom &g = a.geom[f];
         double pw[3];
         int c[3], wn[3];
-        wrap_atom(g, a.raw + 3 * ((long long)f * a.n_atoms + i), pw, c, wn);
+        wrap_atom(g, a.raw + 3 * (a.raw_compact ? (long long)f * per + kk : (long long)f * a.n_atoms + i), pw, c, wn);
         uint32_t dst = a.cell_start[g.cs_off + a.cid[idx]] + a.rank[idx];
         if (a.centre_list) {
             const int cr = a.centre_rank[kk];
