@@ -19,6 +19,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libamofb.so")
+if os.environ.get("AMOFB_LIB"):          # another build of the same library (tools/build_variants.sh), for side-by-side timing
+    _SO = os.path.abspath(os.environ["AMOFB_LIB"])
 
 AMOFB_MAX_SPECIES = 16
 AMOFB_BAD_MAX_CN = 32
