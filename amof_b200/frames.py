@@ -49,7 +49,12 @@ class ArrayTrajectory:
     ``[first_frame, first_frame + len(positions))`` of a trajectory of ``n_frames`` frames (``cells`` always covers all of
     them).  ``len()`` is the length of the whole trajectory, so the analyses shard it exactly as they shard a fully
     resident one (:func:`frame_range`); indexing a frame that is not resident yields an Atoms that carries the atomic
-    numbers, masses and cell but NaN positions."""
+    numbers, masses and cell but NaN positions.
+
+    A subclass that serves its frames from a bounded buffer (``block(a, b)``) may set ``block_frames``: WindowMsd then asks
+    for slabs of at most that many frames."""
+
+    block_frames = None
 
     def __init__(self, numbers, positions, cells, masses=None, pinned=False, first_frame=0, n_frames=None):
         self.pinned = bool(pinned)       # positions live in page-locked memory (Context.pinned_empty): copied as they are

@@ -78,6 +78,8 @@ def _stream_slabs(session, trajectory, lo, hi, backend, distributed):
     T = len(trajectory)
     n = hi - lo
     step = max(1, min(T, session.slab_frames()))
+    if getattr(trajectory, "block_frames", None):       # a trajectory that serves its frames from a bounded buffer says how many at a time
+        step = max(1, min(step, int(trajectory.block_frames)))
     com = np.empty((T, 3), dtype=np.float64)
     is_array = isinstance(trajectory, frames.ArrayTrajectory)
     whole = is_array and lo == 0 and hi == trajectory.positions.shape[1]

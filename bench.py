@@ -476,7 +476,8 @@ class MsdWorkload:
             ctx = self.backend.ctx
             n_local = -(-self.n_total // self.world)         # the library sizes its slabs by the atoms a rank holds
             nslab = max(1, min(self.T, 256, (3 << 29) // (24 * n_local)))
-            nslab = nslab - nslab % 32 if nslab >= 32 else nslab          # the library's own slab size: blocks are served as views
+            nslab = min(nslab, max(32, (2 << 30) // (24 * self.n_total)))   # at most 2 GiB of page-locked host memory per rank
+            nslab = nslab - nslab % 32 if nslab >= 32 else nslab          # whole rounds of the commit kernel; blocks are served as views
             rng = np.random.default_rng(5)
             slabbuf = ctx.pinned_empty((nslab, self.n_total, 3))
             slabbuf[...] = self.pos0[None] + np.cumsum(rng.normal(scale=0.05, size=(nslab, self.n_total, 3)), axis=0)
@@ -488,6 +489,7 @@ class MsdWorkload:
                 def block(self_, a, b):
                     return slabbuf[:b - a] if b - a <= nslab else np.concatenate([slabbuf] * ((b - a) // nslab + 1))[:b - a]
             self.traj = Cyclic(self.numbers, slabbuf, self.cell, masses=self.masses_all, pinned=True, first_frame=0, n_frames=self.T)
+            self.traj.block_frames = nslab                  # WindowMsd then asks for slabs of this many frames
             self._slabbuf = slabbuf
         m = msd.WindowMsd.from_trajectory(self.traj, delta_time=100, timestep=1, mutate=False, distributed=self.world > 1)
         self.last_e2e = m
