@@ -10,7 +10,5 @@ python -c "import __graft_entry__ as g; g.smoke()" > $R/smoke.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $R/launches_bench.csv python bench.py --steps 2 --warmup 3 > $R/ncu_bench.log 2>&1
 python tools/profile_bad.py 2000 3 > $R/bad.log 2>&1
 python tools/profile_msd.py 100000 5000 3 > $R/msd.log 2>&1
-python tools/profile_stream.py 400 > $R/stream.log 2>&1
-tail -2 $R/pytest_gpu.log; cut -c1-400 $R/bench_n1.json; cut -c1-300 $R/bench_ref_n1.json; tail -1 $R/smoke.log; tail -1 $R/bad.log; tail -1 $R/msd.log; tail -3 $R/time_n1.txt $R/time_ref_n1.txt
-# one --set full capture of the bond-angle search kernel as shipped (the pair and MSD captures of this round are of unchanged kernels)
-ncu --set full --clock-control none --import-source on -k regex:k_bad_search -s 3 -c 1 -o $R/prof_bad_search -f python tools/profile_bad.py 900 2 > $R/ncu_bad_search.log 2>&1
+# (python tools/profile_stream.py 400 > $R/stream.log: profiles/r02_stream.txt)
+tail -2 $R/pytest_gpu.log; cut -c1-400 $R/bench_n1.json; cut -c1-300 $R/bench_ref_n1.json; tail -1 $R/smoke.log; tail -1 $R/bad.log; tail -1 $R/msd.log; grep real $R/time_n1.txt $R/time_ref_n1.txt
