@@ -96,6 +96,9 @@ def angle_histograms(trajectory, nb_set_and_cutoff, dtheta, distributed=None, ba
         h, _dropped, _nf = backend.bad_counts(spec, len(zs), frames.iter_chunks(trajectory, lo, hi, backend), cut,
                                               triples, float(dtheta), nbins)
         h = _dist.allreduce_sum(h, distributed)
+        if int(np.sum(_dropped)):
+            # only NaN angles get here (a neighbour on top of its centre): np.histogram drops them silently too (bad.py:160)
+            logger.warning("%d angles of this rank's frames were undefined (zero-length bond) and are not counted", int(np.sum(_dropped)))
         hist[live] = h
     return elements, names, theta_bins, theta, hist
 
