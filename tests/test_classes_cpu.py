@@ -487,3 +487,34 @@ def test_native_xyz_parser_matches_python_float(tmp_path):
                 fh.write("%s %d %r %r %r\n" % (s, a, 0.1 * a + f, 0.2, 0.3 * a))
     s = stream.XyzStream(str(p))
     assert s._pos_col == 2 and np.array_equal(s[1].get_positions(), [[1.0, 0.2, 0.0], [0.1 * 1 + 1, 0.2, 0.3], [0.1 * 2 + 1, 0.2, 0.3 * 2]])
+
+
+def test_native_xyz_index_blocks_and_missing_final_newline(tmp_path):
+    """amofb_xyz_index finds the frame starts across block boundaries exactly as a line count does, and a file whose last line
+    has no newline still parses (the last frame ends at the end of the file)."""
+    from amof_b200 import _lib, stream
+    n = 5
+    lines = []
+    for f in range(7):
+        lines += ["%d" % n, 'Lattice="6 0 0 0 6 0 0 0 6" Properties=species:S:1:pos:R:3'] + ["Zn %r %r %r" % (0.5 * a + f, 1.0, 2.0 + a) for a in range(n)]
+    text = ("\n".join(lines)).encode()            # no final newline
+    want = [0]
+    for i, ch in enumerate(text):
+        if ch == 10 and (text[:i + 1].count(b"\n")) % (n + 2) == 0:
+            want.append(i + 1)
+    # one block, and three blocks cut in the middle of lines
+    starts, nl = _lib.xyz_index(text, 0, n + 2, 0)
+    assert [0] + list(starts) == want and nl == text.count(b"\n")
+    got, before, base = [0], 0, 0
+    for a, b in ((0, 37), (37, 151), (151, len(text))):
+        st, k = _lib.xyz_index(text[a:b], before, n + 2, base)
+        got += list(st)
+        before += k
+        base += b - a
+    assert got == want
+    p = tmp_path / "nonl.xyz"
+    p.write_bytes(text)
+    s = stream.XyzStream(str(p))
+    assert len(s) == 7 and np.array_equal(s[6].get_positions()[:, 0], 0.5 * np.arange(n) + 6)
+    blocks = list(s.stream_chunks(0, 7, None))
+    assert sum(len(b[0]) for b in blocks) == 7 and blocks[-1][0][-1][4][2] == 6.0
