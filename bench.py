@@ -514,7 +514,7 @@ class MsdWorkload:
         peak, how = peaks()
         ach = self.bytes_in / self.world * steps / (dev_ms / 1e3) / 1e9
         pairs = self.units()["atom_frame_pairs_per_step"] / self.world
-        return {"bound": "hbm", "kernel": "k_msd_slab_sums + k_msd_slab_commit + k_msd_window_soa", "achieved": ach, "peak": peak,
+        return {"bound": "hbm", "kernel": "k_msd_slab_sums + k_msd_slab_commit + k_msd_window_wide", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": 4.0 * self.bytes_in / self.world, "peak_source": how,
                 "note": "algorithmic bytes = 24*N*T read once; the path moves 4x that by construction (mass sums read, commit read + "
                         "write of the atom-major store, window read), so 0.25 would be the ceiling of this fraction",
