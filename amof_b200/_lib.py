@@ -92,8 +92,8 @@ SIGNATURES = {
     "amofb_msd_get_positions": (C.c_int, [_vp, _dp]),
     "amofb_msd_end": (C.c_int, [_vp]),
     "amofb_guard_violations": (C.c_int64, [_vp]),
-    "amofb_xyz_index": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _i64p, C.c_int64, _i64p, _i64p]),
-    "amofb_xyz_parse": (C.c_int, [C.c_char_p, _i64p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
+    "amofb_xyz_index": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _i64p, C.c_int64, _i64p, _i64p]),
+    "amofb_xyz_parse": (C.c_int, [_vp, _i64p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, C.c_int, _ip]),
 }
 
 _lib = None
@@ -126,28 +126,37 @@ def _ptr(a, typ):
     return a.ctypes.data_as(typ)
 
 
+def _text_view(text):
+    """bytes, a memory map or a uint8 array -> (uint8 array sharing the memory, its address): nothing is copied"""
+    arr = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+    return arr, arr.ctypes.data
+
+
 def xyz_index(text, lines_before, period, base):
-    """amofb_xyz_index on one block of a file: (file offsets of the frames starting after a newline of this block, newlines seen)"""
+    """amofb_xyz_index on one block of a file (bytes, mmap or uint8 array): (file offsets of the frames starting after a newline of
+    this block, newlines seen)"""
     lib = load_library()
+    text, addr = _text_view(text)
     cap = len(text) // max(1, 2 * int(period)) + 2      # a line is at least 2 bytes
     starts = np.empty(cap, dtype=np.int64)
     n, lines = C.c_int64(0), C.c_int64(0)
-    rc = lib.amofb_xyz_index(text, len(text), int(lines_before), int(period), int(base), _ptr(starts, _i64p), cap, C.byref(n), C.byref(lines))
+    rc = lib.amofb_xyz_index(addr, len(text), int(lines_before), int(period), int(base), _ptr(starts, _i64p), cap, C.byref(n), C.byref(lines))
     if rc != 0:
         raise ValueError("amofb_xyz_index failed (%d)" % rc)
     return starts[:n.value], lines.value
 
 
 def xyz_parse(text, frame_off, n_atoms, pos_col, symbols, symbols_known, out, threads=0):
-    """amofb_xyz_parse (host code of the library: needs no CUDA device).  ``text`` bytes, ``frame_off`` int64[F + 1] offsets into it,
+    """amofb_xyz_parse (host code of the library: needs no CUDA device).  ``text`` bytes / mmap / uint8 array, ``frame_off`` int64[F + 1] offsets into it,
     ``symbols`` a writable bytearray of 8 * n_atoms, ``out`` float64[>= F][n_atoms][3] C-contiguous."""
     lib = load_library()
+    text, addr = _text_view(text)
     frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
     F = len(frame_off) - 1
     assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= F * n_atoms * 3
     bad = C.c_int(-1)
     sym = (C.c_char * len(symbols)).from_buffer(symbols)
-    rc = lib.amofb_xyz_parse(text, _ptr(frame_off, _i64p), F, int(n_atoms), int(pos_col), sym, int(bool(symbols_known)),
+    rc = lib.amofb_xyz_parse(addr, _ptr(frame_off, _i64p), F, int(n_atoms), int(pos_col), sym, int(bool(symbols_known)),
                              _ptr(out, _dp), int(threads), C.byref(bad))
     if rc != 0:
         raise ValueError("XYZ text: frame %d of the block is truncated or malformed, or its atom order differs from the first frame's"

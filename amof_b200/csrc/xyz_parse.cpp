@@ -134,24 +134,68 @@ extern "C" int amofb_xyz_parse(const char *text, const int64_t *frame_off, int n
     return AMOFB_OK;
 }
 
-extern "C" int amofb_xyz_index(const char *text, int64_t len, int64_t lines_before, int64_t period, int64_t base, int64_t *starts,
-                               int64_t capacity, int64_t *n_starts, int64_t *n_lines) {
-    if (!text || len < 0 || period <= 0 || !n_starts || !n_lines || (capacity > 0 && !starts)) return AMOFB_ERR_ARG;
-    int64_t found = 0, lines = 0;
-    int64_t until = period - lines_before % period;       // newlines left before the next frame starts
-    const char *p = text, *end = text + len;
+namespace {
+
+// newlines in [p, end)
+int64_t count_newlines(const char *p, const char *end) {
+    int64_t n = 0;
     while (p < end) {
         const void *q = memchr(p, '\n', (size_t)(end - p));
         if (!q) break;
         p = (const char *)q + 1;
-        ++lines;
+        ++n;
+    }
+    return n;
+}
+
+// frame starts after the newlines of [p, end): `until` newlines are left before the next frame starts
+void emit_starts(const char *text, const char *p, const char *end, int64_t until, int64_t period, int64_t base, std::vector<int64_t> &out) {
+    while (p < end) {
+        const void *q = memchr(p, '\n', (size_t)(end - p));
+        if (!q) break;
+        p = (const char *)q + 1;
         if (--until == 0) {
-            if (found < capacity) starts[found] = base + (p - text);
-            ++found;
+            out.push_back(base + (p - text));
             until = period;
         }
     }
-    *n_starts = found;
-    *n_lines = lines;
-    return found > capacity ? AMOFB_ERR_MEMORY : AMOFB_OK;
+}
+
+}  // namespace
+
+extern "C" int amofb_xyz_index(const char *text, int64_t len, int64_t lines_before, int64_t period, int64_t base, int64_t *starts,
+                               int64_t capacity, int64_t *n_starts, int64_t *n_lines) {
+    if (!text || len < 0 || period <= 0 || !n_starts || !n_lines || (capacity > 0 && !starts)) return AMOFB_ERR_ARG;
+    // large blocks: the host cores count the newlines of a slice each, then -- knowing how many lines precede their slice --
+    // emit the frame starts of it (two memchr passes in parallel instead of one serial one)
+    unsigned hc = std::thread::hardware_concurrency();
+    int threads = (int)(hc ? (hc < 16 ? hc : 16) : 1);
+    if (len < (int64_t)(4 << 20)) threads = 1;
+    std::vector<int64_t> count((size_t)threads, 0);
+    std::vector<std::vector<int64_t>> found((size_t)threads);
+    auto lo = [&](int t) { return text + len * t / threads; };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) pool.emplace_back([&, t]() { count[(size_t)t] = count_newlines(lo(t), lo(t + 1)); });
+        count[0] = count_newlines(lo(0), lo(1));
+        for (auto &th : pool) th.join();
+    }
+    {
+        std::vector<int64_t> before((size_t)threads + 1, lines_before);
+        for (int t = 0; t < threads; ++t) before[(size_t)t + 1] = before[(size_t)t] + count[(size_t)t];
+        std::vector<std::thread> pool;
+        auto run = [&](int t) { emit_starts(text, lo(t), lo(t + 1), period - before[(size_t)t] % period, period, base, found[(size_t)t]); };
+        for (int t = 1; t < threads; ++t) pool.emplace_back(run, t);
+        run(0);
+        for (auto &th : pool) th.join();
+        *n_lines = before[(size_t)threads] - lines_before;
+    }
+    int64_t n = 0;
+    for (auto &v : found)
+        for (int64_t x : v) {
+            if (n < capacity) starts[n] = x;
+            ++n;
+        }
+    *n_starts = n;
+    return n > capacity ? AMOFB_ERR_MEMORY : AMOFB_OK;
 }

@@ -11,8 +11,8 @@ trajectory.py:193-228).  End to end that list is the bottleneck, 
     the library's native parser (``amofb_xyz_parse``, all host cores) fills into a ring of page-locked buffers ahead of the consumer,
     so chunk k+1.. are being parsed while chunk k is copied and counted.
 
-One pass over the file finds where every frame starts (newline counting on raw bytes, vectorised); gzipped files are
-inflated to a temporary file first, as ``Trajectory.from_traj(unzip=True)`` does.
+The file is memory-mapped; one parallel pass (``amofb_xyz_index``) finds where every frame starts; gzipped files are inflated
+to a temporary file first, as ``Trajectory.from_traj(unzip=True)`` does.
 """
 import gzip
 import logging
@@ -29,23 +29,20 @@ from .elements import atomic_numbers
 logger = logging.getLogger(__name__)
 
 
-def _frame_offsets(path, period):
-    """byte offset of the first line of every frame (a frame = ``period`` lines), and the file size"""
-    from . import _lib
+def _map_file(path):
+    """the file as a read-only uint8 array (memory-mapped: the index and the parser read the page cache in place)"""
     size = os.path.getsize(path)
-    starts = [np.zeros(1, dtype=np.int64)]
-    lines_before = 0
-    with open(path, "rb") as fh:
-        base = 0
-        while True:
-            buf = fh.read(64 << 20)
-            if not buf:
-                break
-            found, lines = _lib.xyz_index(buf, lines_before, period, base)
-            starts.append(found)
-            lines_before += lines
-            base += len(buf)
-    offs = np.concatenate(starts)
+    if size == 0:
+        return np.zeros(0, dtype=np.uint8)
+    return np.memmap(path, dtype=np.uint8, mode="r")
+
+
+def _frame_offsets(data, period):
+    """byte offset of the first line of every frame (a frame = ``period`` lines) of the mapped file, and its size"""
+    from . import _lib
+    size = len(data)
+    found, _lines = _lib.xyz_index(data, 0, period, 0) if size else (np.zeros(0, dtype=np.int64), 0)
+    offs = np.concatenate([np.zeros(1, dtype=np.int64), found])
     offs = offs[offs < size]                       # a trailing newline does not start a frame
     return offs, size
 
@@ -85,7 +82,8 @@ class XyzStream(object):
                 if name == 'pos':
                     self._pos_col = col
                 col += int(width)
-        offs, size = _frame_offsets(self.path, self._period)
+        self._data = _map_file(self.path)
+        offs, size = _frame_offsets(self._data, self._period)
         self._offs_all = np.append(offs, size)
         n_file = len(offs)
         sel = np.arange(n_file)
@@ -140,25 +138,20 @@ class XyzStream(object):
             out = np.empty((len(ids), n, 3))
         known = getattr(self, "_symbytes", None) is not None
         symbytes = self._symbytes if known else bytearray(8 * n)
-        with open(self.path, "rb") as fh:
-            i = 0
-            while i < len(ids):                   # consecutive file frames are one read and one call
-                j = i
-                while j + 1 < len(ids) and ids[j + 1] == ids[j] + 1:
-                    j += 1
-                a, b = int(ids[i]), int(ids[j])
-                base = int(self._offs_all[a])
-                fh.seek(base)
-                buf = fh.read(int(self._offs_all[b + 1]) - base)
-                if len(buf) != int(self._offs_all[b + 1]) - base:
-                    raise ValueError("truncated XYZ file")
-                try:
-                    _lib.xyz_parse(buf, self._offs_all[a:b + 2] - base, n, self._pos_col, symbytes, known, out[i:j + 1],
-                                   threads=threads)
-                except ValueError as err:
-                    raise ValueError("%s: %s (block starting at file frame %d)" % (self.path, err, a))
-                known = True
-                i = j + 1
+        i = 0
+        while i < len(ids):                       # consecutive file frames are one call on the mapped file
+            j = i
+            while j + 1 < len(ids) and ids[j + 1] == ids[j] + 1:
+                j += 1
+            a, b = int(ids[i]), int(ids[j])
+            base, end = int(self._offs_all[a]), int(self._offs_all[b + 1])
+            try:
+                _lib.xyz_parse(self._data[base:end], self._offs_all[a:b + 2] - base, n, self._pos_col, symbytes, known, out[i:j + 1],
+                               threads=threads)
+            except ValueError as err:
+                raise ValueError("%s: %s (block starting at file frame %d)" % (self.path, err, a))
+            known = True
+            i = j + 1
         if getattr(self, "_symbytes", None) is None:
             self._symbytes = symbytes
         symbols = [bytes(symbytes[8 * k:8 * k + 8]).rstrip(b"\0").decode() for k in range(n)] if len(ids) else []
@@ -224,6 +217,7 @@ class XyzStream(object):
                     submit()
 
     def close(self):
+        self._data = None                       # drops the memory map
         if self._tmp is not None:
             self._tmp.close()
             self._tmp = None
