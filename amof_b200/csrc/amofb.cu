@@ -429,7 +429,7 @@ static int batcher_set_filter(amofb_ctx *ctx, Batcher &b, const uint8_t *species
         }
     }
     // frames in host memory: when under 60 % of the atoms are kept, host threads gather them and only they are copied (C4 'Zn-N':
-    // 29 % of 1.175 MB per frame; the kept atoms are single atoms between others, so a strided DMA would not do)
+    // 29 % of 1.175 MB per frame; the kept atoms come in runs of ten between others, too short for a strided DMA)
     b.keep_host = idx;
     b.gather = !idx.empty() && 10 * (long long)idx.size() < 6 * (long long)b.n_atoms && !env_int("AMOFB_NO_HOST_GATHER", 0);
     AMOFB_TRY(dev_alloc(ctx, &b.d_species_keep, (size_t)AMOFB_MAX_SPECIES));
