@@ -41,9 +41,14 @@ def _frame_offsets(data, period):
     """byte offset of the first line of every frame (a frame = ``period`` lines) of the mapped file, and its size"""
     from . import _lib
     size = len(data)
-    found, _lines = _lib.xyz_index(data, 0, period, 0) if size else (np.zeros(0, dtype=np.int64), 0)
+    while size > 0 and data[size - 1] in (10, 13, 32, 9):      # blank space after the last atom line is not part of a frame
+        size -= 1
+    if size == 0:
+        return np.zeros(0, dtype=np.int64), 0
+    found, lines = _lib.xyz_index(data[:size], 0, period, 0)
+    if (lines + 1) % period != 0:
+        raise ValueError("truncated XYZ file: %d lines are not a whole number of frames of %d lines" % (lines + 1, period))
     offs = np.concatenate([np.zeros(1, dtype=np.int64), found])
-    offs = offs[offs < size]                       # a trailing newline does not start a frame
     return offs, size
 
 

@@ -518,3 +518,16 @@ def test_native_xyz_index_blocks_and_missing_final_newline(tmp_path):
     assert len(s) == 7 and np.array_equal(s[6].get_positions()[:, 0], 0.5 * np.arange(n) + 6)
     blocks = list(s.stream_chunks(0, 7, None))
     assert sum(len(b[0]) for b in blocks) == 7 and blocks[-1][0][-1][4][2] == 6.0
+
+
+def test_stream_refuses_truncated_files_and_ignores_trailing_blank_lines(tmp_path):
+    from amof_b200 import stream
+    frame = '2\nLattice="5 0 0 0 5 0 0 0 5"\nZn 0 0 0\nN %d 1 1\n'
+    p = tmp_path / "trunc.xyz"
+    p.write_text(frame % 1 + frame[:-10] % 2)
+    with pytest.raises(ValueError, match="truncated"):
+        stream.XyzStream(str(p))
+    q = tmp_path / "blank.xyz"
+    q.write_text(frame % 1 + frame % 2 + "\n\n  \n")
+    s = stream.XyzStream(str(q))
+    assert len(s) == 2 and s[1].get_positions()[1, 0] == 2.0
