@@ -524,7 +524,7 @@ def test_stream_refuses_truncated_files_and_ignores_trailing_blank_lines(tmp_pat
     from amof_b200 import stream
     frame = '2\nLattice="5 0 0 0 5 0 0 0 5"\nZn 0 0 0\nN %d 1 1\n'
     p = tmp_path / "trunc.xyz"
-    p.write_text(frame % 1 + frame[:-10] % 2)
+    p.write_text(frame % 1 + '2\nLattice="5 0 0 0 5 0 0 0 5"\nZn 0 0 0\n')
     with pytest.raises(ValueError, match="truncated"):
         stream.XyzStream(str(p))
     q = tmp_path / "blank.xyz"
