@@ -381,7 +381,7 @@ static int batcher_init(amofb_ctx *ctx, Batcher &b, int n_atoms, const uint8_t *
     cap = std::min<long long>(cap, (1ll << 30) / (24ll * std::max(n_atoms, 1)));
     b.cap_frames = (int)std::min<long long>(std::max<long long>(cap, 1), 8192);
     if (max_frames > 0 && b.cap_frames > max_frames) b.cap_frames = max_frames;
-    b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0 * AMOFB_MAX_SPECIES) + 1;      // per list at most 4 cells per atom + 64 (host_fill_geom)
+    b.cells_per_frame = (size_t)(4.0 * n_atoms + 64.0 * AMOFB_MAX_SPECIES) + 4;      // per list at most 4 cells per atom + 64 (host_fill_geom)
     AMOFB_TRY(dev_alloc(ctx, &b.d_species, (size_t)n_atoms));
     CUDA_TRY(ctx, cudaMemcpy(b.d_species, species, (size_t)n_atoms, cudaMemcpyHostToDevice));
     size_t na = (size_t)b.cap_frames * n_atoms;
@@ -456,6 +456,10 @@ static int batcher_harvest(amofb_ctx *ctx, Batcher &b, BatchSlot &s) {
 #ifndef HOST_GATHER_AHEAD
 #define HOST_GATHER_AHEAD 64        // measured on C4 (16 threads): none 59-61 k, 8 ahead 66-69 k, 64 ahead 70-72 k frames/s end to end
 #endif
+// entries a frame takes in the batch-wide cell_count / cell_start arrays: its n_lists * ncell + 1 counters rounded up to 16 bytes, so
+// that every frame's array starts aligned and k_cell_scan takes its 16-byte path (with the odd natural size three frames in four did not)
+static inline int cs_stride(int n_lists, int ncell) { return (n_lists * ncell + 1 + 3) & ~3; }
+
 // out[f][k] = pos[f][keep[k]] for nf frames, split over host threads by frame
 static void host_gather_atoms(const double *pos, int nf, int n_atoms, const std::vector<int> &keep, double *out) {
     const size_t nk = keep.size();
@@ -496,7 +500,7 @@ static int batcher_stage(amofb_ctx *ctx, Batcher &b, int nf, const double *pos, 
                               (long long)(b.frames_seen + f), b.rcut);
         g.cs_off = cs_off;
         g.frame_id = (int)(b.frames_seen + f);
-        cs_off += b.n_lists * g.ncell + 1;
+        cs_off += cs_stride(b.n_lists, g.ncell);
         b.volume_sum += host_cell_volume(cell + 9 * (size_t)f);
     }
     const double *raw = pos;
@@ -833,7 +837,7 @@ static int pair_push_impl(amofb_ctx *ctx, int n_frames, const double *pos, bool 
                 int R = (g.m[1] + 1) + g.m[0] * (2 * g.m[1] + 1);
                 if (R > TILE_MAX_ROWS || TILE_MAX_ENTRIES / R < 2 * g.m[2] + 1) tiled = false;
                 if (g.m[0] > g.nc[0] || g.m[1] > g.nc[1] || g.m[2] > g.nc[2]) tiled = false;     // image shifts beyond +-1 cell vector: generic kernel
-                ncell_total += (size_t)g.ncell + 1;
+                ncell_total += (size_t)cs_stride(1, g.ncell);
                 columns += (long long)g.nc[0] * g.nc[1];
             }
             if (tiled) {
